@@ -1,0 +1,53 @@
+// fcfc_b200/csrc/dispatch.h -- maps the runtime description of a count onto one of the compiled
+// kernel variants.  The reference selects one of 384 macro-generated functions at this point
+// (src/fcfc/2pt_box/count_func.c:4871-7141); here the lookup-table width, table type and the
+// non-zero lower bounds are handled at run time inside a "generic" variant, which leaves
+// precision x binning x metric x weights x arithmetic order x {fast, generic, global-histogram}.
+#pragma once
+#include "count_kernel.cuh"
+
+namespace fcfc {
+
+struct Variant {
+  bool is_float, box, wt, generic, smem_hist;
+  int bintype, arith;
+};
+
+constexpr int kR = 4;   // primary points per lane
+
+// Defined (explicitly instantiated) in the generated inst_*.cu files.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST>
+cudaError_t launch_variant(const CountParams<T> &P, int nblocks, int smem_bytes);
+
+template <class T, int BIN, bool BOX, bool WT, int ARITH>
+static cudaError_t launch_l3(const Variant &v, const CountParams<T> &P, int nb, int sm) {
+  if (!v.smem_hist) return launch_variant<T, BIN, BOX, WT, ARITH, true, false>(P, nb, sm);
+  if (v.generic) return launch_variant<T, BIN, BOX, WT, ARITH, true, true>(P, nb, sm);
+  return launch_variant<T, BIN, BOX, WT, ARITH, false, true>(P, nb, sm);
+}
+template <class T, int BIN, bool BOX>
+static cudaError_t launch_l2(const Variant &v, const CountParams<T> &P, int nb, int sm) {
+  if (v.wt) return v.arith ? launch_l3<T, BIN, BOX, true, 1>(v, P, nb, sm) : launch_l3<T, BIN, BOX, true, 0>(v, P, nb, sm);
+  return v.arith ? launch_l3<T, BIN, BOX, false, 1>(v, P, nb, sm) : launch_l3<T, BIN, BOX, false, 0>(v, P, nb, sm);
+}
+template <class T>
+static cudaError_t launch_count(const Variant &v, const CountParams<T> &P, int nb, int sm) {
+  switch (v.bintype) {
+    case BIN_ISO: return v.box ? launch_l2<T, BIN_ISO, true>(v, P, nb, sm) : launch_l2<T, BIN_ISO, false>(v, P, nb, sm);
+    case BIN_SMU: return v.box ? launch_l2<T, BIN_SMU, true>(v, P, nb, sm) : launch_l2<T, BIN_SMU, false>(v, P, nb, sm);
+    default: return v.box ? launch_l2<T, BIN_SPI, true>(v, P, nb, sm) : launch_l2<T, BIN_SPI, false>(v, P, nb, sm);
+  }
+}
+
+// Body used by the generated instantiation files.
+#define FCFC_DEFINE_VARIANT(T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST)                                   \
+  template <> cudaError_t launch_variant<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST>(                     \
+      const CountParams<T> &P, int nblocks, int smem_bytes) {                                            \
+    auto kern = count_kernel<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, kR>;                             \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<nblocks, kThreads, smem_bytes>>>(P);                                                          \
+    return cudaGetLastError();                                                                           \
+  }
+
+}  // namespace fcfc

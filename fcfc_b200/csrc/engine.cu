@@ -1,0 +1,665 @@
+// fcfc_b200/csrc/engine.cu -- host side of libfcfc_b200.so: the C ABI of include/fcfc_gpu.h.
+//
+// Replaces tree_create / tree_destroy / count_pairs of the reference
+// (src/fcfc/2pt_box/build_tree.c:36-219, count_func.c:4847-7724 and the survey twins) with
+//   catalogue upload -> cell list (cell index, radix sort, gather)   [replaces src/tree/*.c]
+//   neighbour stencil + work items -> persistent counting kernel      [replaces dual_tree.c,
+//                                                                       metric_*.c, OpenMP/MPI]
+// There is no CPU fallback anywhere in this file: without a usable device every call fails.
+#include "../../include/fcfc_gpu.h"
+#include "count_kernel.cuh"
+#include "dispatch.h"
+
+#include <cub/cub.cuh>
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+namespace fcfc {
+
+// ------------------------------------------------------------------------------------------
+// error handling
+static thread_local std::string g_err;
+static thread_local fcfc_gpu_stats g_stats;
+static int g_verbose = 0;
+
+static void set_err(const char *fmt, ...) {
+  char buf[1024];
+  va_list ap; va_start(ap, fmt); vsnprintf(buf, sizeof buf, fmt, ap); va_end(ap);
+  g_err = buf;
+  if (g_verbose) fprintf(stderr, "[fcfc_gpu] error: %s\n", buf);
+}
+#define CUDA_TRY(x, code)                                                                \
+  do { cudaError_t e_ = (x); if (e_ != cudaSuccess) {                                    \
+    set_err("%s failed at %s:%d: %s", #x, __FILE__, __LINE__, cudaGetErrorString(e_));   \
+    cudaGetLastError(); return code; } } while (0)
+
+// ------------------------------------------------------------------------------------------
+// device context (one per process; multi-GPU jobs run one process per GPU, or list several
+// devices here and let fcfc_gpu_count loop over them)
+struct Context {
+  std::vector<int> devices;
+  int sm_count = 0;
+  bool ready = false;
+};
+static Context g_ctx;
+
+static int ensure_init() {
+  if (g_ctx.ready) return 0;
+  return fcfc_gpu_init(0, nullptr, 0) > 0 ? 0 : FCFC_GPU_ERR_CUDA;
+}
+
+// ------------------------------------------------------------------------------------------
+// cell grid
+struct Grid {
+  int nc[3] = {1, 1, 1};
+  double origin[3] = {0, 0, 0};
+  double cs[3] = {0, 0, 0};     // cell size
+  double box[3] = {0, 0, 0};    // periodic box (0 if not periodic)
+  int periodic = 0;
+  bool operator==(const Grid &o) const {
+    return !memcmp(nc, o.nc, sizeof nc) && !memcmp(origin, o.origin, sizeof origin) &&
+           !memcmp(cs, o.cs, sizeof cs) && !memcmp(box, o.box, sizeof box) && periodic == o.periodic;
+  }
+  long long ncell() const { return (long long) nc[0] * nc[1] * nc[2]; }
+};
+
+template <class T> struct Sorted {
+  bool valid = false;
+  Grid grid;
+  int tile = 0;                 // points per work item
+  Vec4<T> *pos = nullptr;
+  T *w = nullptr;
+  int *cell_start = nullptr;    // ncell + 1
+  int *item_cell = nullptr, *item_off = nullptr, *item_cnt = nullptr;
+  int nitem = 0;
+  void release() {
+    cudaFree(pos); cudaFree(w); cudaFree(cell_start); cudaFree(item_cell); cudaFree(item_off); cudaFree(item_cnt);
+    pos = nullptr; w = nullptr; cell_start = nullptr; item_cell = item_off = item_cnt = nullptr;
+    valid = false; nitem = 0;
+  }
+};
+
+}  // namespace fcfc
+
+struct fcfc_gpu_catalog {
+  int is_float = 0;
+  size_t n = 0;
+  int device = 0;
+  void *x = nullptr, *y = nullptr, *z = nullptr, *s = nullptr, *w = nullptr;   // device SoA of `real`
+  bool has_s = false, has_w = false;
+  double bmin[3], bmax[3];      // bounding box of the (rescaled) coordinates
+  double smax = 0;              // max of x^2+y^2+z^2
+  double wsum = 0;
+  fcfc::Sorted<float> sf;
+  fcfc::Sorted<double> sd;
+};
+
+namespace fcfc {
+
+template <class T> static Sorted<T> &sorted_of(fcfc_gpu_catalog *c);
+template <> Sorted<float> &sorted_of<float>(fcfc_gpu_catalog *c) { return c->sf; }
+template <> Sorted<double> &sorted_of<double>(fcfc_gpu_catalog *c) { return c->sd; }
+
+// ------------------------------------------------------------------------------------------
+// catalogue kernels
+__device__ __forceinline__ unsigned long long enc_f64(double v) {       // order-preserving encoding
+  unsigned long long u = (unsigned long long) __double_as_longlong(v);
+  return (u & 0x8000000000000000ull) ? ~u : (u | 0x8000000000000000ull);
+}
+static inline double dec_f64(unsigned long long u) {
+  u = (u & 0x8000000000000000ull) ? (u & 0x7fffffffffffffffull) : ~u;
+  double d; memcpy(&d, &u, 8); return d;
+}
+
+// stats[0..2] = min xyz, [3..5] = max xyz, [6] = max s (all order-encoded), [7] = #non-finite
+// Rescales in `real` precision (build_tree.c:121-131) and, when requested, fills the survey's 4th
+// coordinate (2pt/build_tree.c:59 scalar order / :75-82 FMA order).
+template <class T>
+__global__ void prep_kernel(T *x, T *y, T *z, T *s, size_t n, T rescale, int do_rescale, int sumsq,
+                            unsigned long long *stats, double *wsum, const T *w) {
+  using A = Ar<T>;
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, smx = 0, ws = 0;
+  unsigned long long bad = 0;
+  for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
+    T a = x[i], b = y[i], c = z[i];
+    if (do_rescale) { a = A::mul(a, rescale); b = A::mul(b, rescale); c = A::mul(c, rescale); x[i] = a; y[i] = b; z[i] = c; }
+    T ss;
+    if (sumsq == 0) ss = A::add(A::add(A::mul(a, a), A::mul(b, b)), A::mul(c, c));
+    else if (sumsq == 1) ss = A::fma(c, c, A::fma(b, b, A::mul(a, a)));
+    else ss = s ? s[i] : A::add(A::add(A::mul(a, a), A::mul(b, b)), A::mul(c, c));
+    if (sumsq >= 0 && s) s[i] = ss;
+    if (!(isfinite((double) a) && isfinite((double) b) && isfinite((double) c))) { bad++; continue; }
+    mn[0] = fmin(mn[0], (double) a); mn[1] = fmin(mn[1], (double) b); mn[2] = fmin(mn[2], (double) c);
+    mx[0] = fmax(mx[0], (double) a); mx[1] = fmax(mx[1], (double) b); mx[2] = fmax(mx[2], (double) c);
+    smx = fmax(smx, (double) ss);
+    if (w) ws += (double) w[i];
+  }
+  typedef cub::BlockReduce<double, 256> BR;
+  typedef cub::BlockReduce<unsigned long long, 256> BRU;
+  __shared__ typename BR::TempStorage tmp;
+  __shared__ typename BRU::TempStorage tmpu;
+  for (int k = 0; k < 3; k++) {
+    double v = BR(tmp).Reduce(mn[k], cub::Min()); __syncthreads();
+    if (threadIdx.x == 0) atomicMin(&stats[k], enc_f64(v));
+    v = BR(tmp).Reduce(mx[k], cub::Max()); __syncthreads();
+    if (threadIdx.x == 0) atomicMax(&stats[3 + k], enc_f64(v));
+  }
+  double v = BR(tmp).Reduce(smx, cub::Max()); __syncthreads();
+  if (threadIdx.x == 0) atomicMax(&stats[6], enc_f64(v));
+  v = BR(tmp).Sum(ws); __syncthreads();
+  if (threadIdx.x == 0 && w) atomicAdd(wsum, v);
+  unsigned long long nb = BRU(tmpu).Sum(bad);
+  if (threadIdx.x == 0 && nb) atomicAdd(&stats[7], nb);
+}
+
+// cell id of every point (double arithmetic so that float and double catalogues bin identically)
+template <class T>
+__global__ void cellid_kernel(const T *x, const T *y, const T *z, int n, Grid g, unsigned int *key, int *idx, int *err) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double p[3] = {(double) x[i], (double) y[i], (double) z[i]};
+  int c[3];
+#pragma unroll
+  for (int k = 0; k < 3; k++) {
+    double u = (p[k] - g.origin[k]) / g.cs[k];
+    int ci = (int) floor(u);
+    if (g.periodic && !(p[k] >= 0 && p[k] <= g.box[k])) atomicExch(err, 1);   // x == L happens after rounding to float
+    c[k] = min(max(ci, 0), g.nc[k] - 1);
+  }
+  key[i] = (unsigned int) ((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+  idx[i] = i;
+}
+
+template <class T>
+__global__ void gather_kernel(const T *x, const T *y, const T *z, const T *s, const T *w, const int *idx, int n,
+                              Vec4<T> *pos, T *wout) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int j = idx[i];
+  Vec4<T> v; v.x = x[j]; v.y = y[j]; v.z = z[j]; v.s = s ? s[j] : (T) 0;
+  pos[i] = v;
+  if (wout) wout[i] = w ? w[j] : (T) 1;
+}
+
+// cell_start[c] = first sorted index with key >= c (keys sorted ascending), cell_start[ncell] = n
+__global__ void cellstart_kernel(const unsigned int *key, int n, int ncell, int *cell_start) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > n) return;
+  int prev = (i == 0) ? -1 : (int) key[i - 1];
+  int cur = (i == n) ? ncell : (int) key[i];
+  for (int c = prev + 1; c <= cur; c++) cell_start[c] = i;
+}
+
+// number of tiles per cell (balanced split of the cell into ceil(n/tile) items)
+__global__ void ntile_kernel(const int *cell_start, int ncell, int tile, int *ntile) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int n = cell_start[c + 1] - cell_start[c];
+  ntile[c] = (n + tile - 1) / tile;
+}
+__global__ void items_kernel(const int *cell_start, const int *tile_off, int ncell, int tile,
+                             int *item_cell, int *item_off, int *item_cnt) {
+  int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= ncell) return;
+  int b = cell_start[c], n = cell_start[c + 1] - b;
+  if (n == 0) return;
+  int nt = (n + tile - 1) / tile, o = tile_off[c];
+  int base = n / nt, rem = n % nt, p = b;
+  for (int t = 0; t < nt; t++) {
+    int m = base + (t < rem ? 1 : 0);
+    item_cell[o + t] = c; item_off[o + t] = p; item_cnt[o + t] = m;
+    p += m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool need_w, float *ms_out) {
+  Sorted<T> &S = sorted_of<T>(cat);
+  if (S.valid && S.grid == g && S.tile == tile && (!need_w || S.w)) return 0;
+  S.release();
+  const int n = (int) cat->n;
+  const long long ncell = g.ncell();
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
+  unsigned int *key = nullptr, *key2 = nullptr; int *idx = nullptr, *idx2 = nullptr, *err = nullptr;
+  int *ntile = nullptr, *tile_off = nullptr; void *tmp = nullptr;
+  auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(idx); cudaFree(idx2); cudaFree(err); cudaFree(ntile); cudaFree(tile_off); cudaFree(tmp); };
+#define TRY_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err("%s: %s", #x, cudaGetErrorString(e_)); cudaGetLastError(); cleanup(); S.release(); return FCFC_GPU_ERR_TREE; } } while (0)
+  const size_t nn = n ? n : 1;
+  TRY_(cudaMalloc(&key, nn * 4)); TRY_(cudaMalloc(&key2, nn * 4)); TRY_(cudaMalloc(&idx, nn * 4)); TRY_(cudaMalloc(&idx2, nn * 4));
+  TRY_(cudaMalloc(&err, 4)); TRY_(cudaMemset(err, 0, 4));
+  TRY_(cudaMalloc(&S.pos, nn * sizeof(Vec4<T>)));
+  if (need_w) TRY_(cudaMalloc(&S.w, nn * sizeof(T)));
+  TRY_(cudaMalloc(&S.cell_start, (ncell + 1) * sizeof(int)));
+  const int nb = (n + 255) / 256;
+  if (n) {
+    cellid_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z, n, g, key, idx, err);
+    g_stats.kernel_launches++;
+    int bits = 1; while ((1ll << bits) < ncell) bits++;
+    size_t tb = 0;
+    TRY_(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, idx, idx2, n, 0, bits));
+    TRY_(cudaMalloc(&tmp, tb ? tb : 1));
+    TRY_(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, idx, idx2, n, 0, bits));
+    gather_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z,
+                                  cat->has_s ? (const T *) cat->s : nullptr, cat->has_w ? (const T *) cat->w : nullptr,
+                                  idx2, n, S.pos, S.w);
+    g_stats.kernel_launches += 2;
+  }
+  cellstart_kernel<<<(n + 1 + 255) / 256, 256>>>(key2, n, (int) ncell, S.cell_start);
+  g_stats.kernel_launches++;
+  int herr = 0;
+  TRY_(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
+  if (herr) {
+    set_err("catalogue has points outside the periodic box: FCFC_2PT_BOX expects 0 <= x <= BOX_SIZE");
+    cleanup(); S.release(); return FCFC_GPU_ERR_DATA;
+  }
+  // work items
+  TRY_(cudaMalloc(&ntile, (ncell + 1) * sizeof(int))); TRY_(cudaMalloc(&tile_off, (ncell + 1) * sizeof(int)));
+  TRY_(cudaMemset(ntile, 0, (ncell + 1) * sizeof(int)));
+  ntile_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, (int) ncell, tile, ntile);
+  cudaFree(tmp); tmp = nullptr;
+  size_t tb = 0;
+  TRY_(cub::DeviceScan::ExclusiveSum(nullptr, tb, ntile, tile_off, (int) ncell + 1));
+  TRY_(cudaMalloc(&tmp, tb ? tb : 1));
+  TRY_(cub::DeviceScan::ExclusiveSum(tmp, tb, ntile, tile_off, (int) ncell + 1));
+  int nitem = 0;
+  TRY_(cudaMemcpy(&nitem, tile_off + ncell, 4, cudaMemcpyDeviceToHost));
+  S.nitem = nitem;
+  const size_t ni = nitem ? nitem : 1;
+  TRY_(cudaMalloc(&S.item_cell, ni * 4)); TRY_(cudaMalloc(&S.item_off, ni * 4)); TRY_(cudaMalloc(&S.item_cnt, ni * 4));
+  items_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, tile_off, (int) ncell, tile, S.item_cell, S.item_off, S.item_cnt);
+  g_stats.kernel_launches += 3;
+  TRY_(cudaGetLastError());
+  cudaEventRecord(e1); TRY_(cudaEventSynchronize(e1));
+  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (ms_out) *ms_out += ms;
+  cudaEventDestroy(e0); cudaEventDestroy(e1);
+  cleanup();
+#undef TRY_
+  S.valid = true; S.grid = g; S.tile = tile;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Search radii.  The cell sweep must cover every pair the per-pair tests can accept, including
+// pairs that only pass because of rounding in `real` arithmetic, hence the small inflation.
+struct Reach { double r2_xy, r_z; bool cylinder; double r2; };
+
+static Reach compute_reach(const fcfc_gpu_bins *b, double s2max, double pmax, double maxabs, double smax_sq, bool is_float) {
+  const double eps = is_float ? FLT_EPSILON : DBL_EPSILON;
+  Reach R;
+  R.cylinder = (b->periodic && b->bintype == FCFC_GPU_BIN_SPI);
+  double slack;
+  if (b->periodic || b->bintype == FCFC_GPU_BIN_ISO) slack = 64 * eps * maxabs * maxabs;
+  else slack = 64 * eps * (smax_sq + 1);          // survey: s^2 by cancellation of |x|^2-sized terms
+  if (R.cylinder) {
+    R.r2_xy = s2max * (1 + 1e-6) + slack;
+    R.r_z = pmax * (1 + 1e-6) + 64 * eps * maxabs;
+    R.r2 = R.r2_xy + R.r_z * R.r_z;
+  } else {
+    double r2 = s2max;
+    if (!b->periodic && b->bintype == FCFC_GPU_BIN_SPI) r2 = s2max + pmax;   // pmax is pi^2 here (count_func.c:5296)
+    R.r2 = r2 * (1 + 1e-6) + slack;
+    R.r2_xy = R.r2; R.r_z = std::sqrt(R.r2);
+  }
+  return R;
+}
+
+// Stencil rows (dx, dy, zlo, zhi) of the cells that can hold a pair within reach.  For auto counts
+// only the lexicographically positive half is kept (every unordered cell pair once).
+static std::vector<int4> build_stencil(const Grid &g, const Reach &R, bool half) {
+  std::vector<int4> rows;
+  auto gap = [](int d, double cs) { int a = std::abs(d) - 1; return a > 0 ? a * cs : 0.0; };
+  const double rxy = std::sqrt(R.r2_xy);
+  const int kx = (int) std::ceil(rxy / g.cs[0]) + 1, ky = (int) std::ceil(rxy / g.cs[1]) + 1;
+  for (int dx = -kx; dx <= kx; dx++)
+    for (int dy = -ky; dy <= ky; dy++) {
+      if (half && (dx < 0 || (dx == 0 && dy < 0))) continue;
+      double gx = gap(dx, g.cs[0]), gy = gap(dy, g.cs[1]);
+      double d2 = gx * gx + gy * gy;
+      if (d2 >= R.r2_xy) continue;
+      int zmax = 0;
+      while (true) {
+        double gz = gap(zmax + 1, g.cs[2]);
+        bool ok = R.cylinder ? (gz < R.r_z) : (d2 + gz * gz < R.r2);
+        if (!ok) break;
+        zmax++;
+      }
+      // NB: no clamping to nc/2 on periodic axes: offsets d and d - nc address the same cell through
+      // *different* periodic images, and both can hold in-range pairs; the gap test alone prunes.
+      int zlo = -zmax, zhi = zmax;
+      if (half && dx == 0 && dy == 0) { zlo = 1; if (zhi < zlo) continue; }
+      rows.push_back(make_int4(dx, dy, zlo, zhi));
+    }
+  return rows;
+}
+
+// Choose the number of cells: cells of side reach/k, k picked by a simple cost model
+// (candidate evaluations per primary point, tile fill of the primary cells, per-range overhead).
+static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[3], const double hi[3],
+                        double n1, double n2, int tile, bool half) {
+  Grid best; double best_cost = 1e300;
+  const double rxy = std::sqrt(R.r2_xy), rz = R.r_z;
+  for (int k = 1; k <= 12; k++) {
+    Grid g; g.periodic = b->periodic;
+    bool ok = true;
+    for (int d = 0; d < 3; d++) {
+      const double want = ((d == 2) ? rz : rxy) / k;
+      if (b->periodic) {
+        const double L = b->bsize[d];
+        int nc = (int) std::floor(L / want);
+        if (nc < 1) nc = 1;
+        while (nc > 1 && L / nc < want) nc--;
+        g.nc[d] = nc; g.origin[d] = 0; g.cs[d] = L / nc; g.box[d] = L;
+      } else {
+        const double ext = std::max(hi[d] - lo[d], 1e-30);
+        int nc = (int) std::floor(ext / want) + 1;
+        g.nc[d] = nc; g.origin[d] = lo[d]; g.cs[d] = want;
+      }
+      if (g.nc[d] > 2048) ok = false;
+    }
+    if (!ok || g.ncell() > (1ll << 26)) break;
+    const double ncell = (double) g.ncell();
+    const double m1 = std::max(n1 / ncell, 1e-3), m2 = std::max(n2 / ncell, 1e-3);
+    std::vector<int4> st = build_stencil(g, R, half);
+    double cand = 0, nseg = 0;
+    for (auto &r : st) { double pts = (r.w - r.z + 1) * m2; cand += std::ceil(pts / 32) * 32 + 24; nseg += 1; }
+    if (half) cand += m2 / 2 + 24;
+    const double tiles = std::ceil(m1 / tile);
+    const double fill = m1 / (tiles * tile);
+    const double cost = cand / std::min(1.0, fill + 1e-9) + 1e-3 * ncell / std::max(n1, 1.0);
+    if (g_verbose > 1) fprintf(stderr, "[fcfc_gpu] k=%d nc=%dx%dx%d rows=%zu m1=%.1f cand=%.0f fill=%.2f cost=%.0f\n", k, g.nc[0], g.nc[1], g.nc[2], st.size(), m1, cand, fill, cost);
+    if (cost < best_cost && st.size() <= (size_t) kMaxRows) { best_cost = cost; best = g; }
+    if (m1 < 4 && m2 < 4) break;
+  }
+  return best;
+}
+
+// ------------------------------------------------------------------------------------------
+template <class T>
+static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
+                      int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
+  const bool is_float = sizeof(T) == 4;
+  const int bintype = b->bintype;
+  const int ns = b->ns, np = (bintype == BIN_SPI) ? b->np : 0, nmu = (bintype == BIN_SMU) ? b->nmu : 1;
+  const size_t ntot = (size_t) ns * (bintype == BIN_ISO ? 1 : (bintype == BIN_SMU ? nmu : np));
+  if (ns < 1 || ntot < 1 || !b->s2bin || !b->stab) { set_err("invalid bins"); return FCFC_GPU_ERR_ARG; }
+  if (bintype == BIN_SPI && (!b->pbin || !b->ptab || np < 1)) { set_err("(s_perp, pi) bins need pbin/ptab"); return FCFC_GPU_ERR_ARG; }
+  if (bintype == BIN_SMU && (!b->mutab || nmu < 1)) { set_err("(s, mu) bins need mutab"); return FCFC_GPU_ERR_ARG; }
+  if (!b->periodic && bintype != BIN_ISO && (!c1->has_s || !c2->has_s)) { set_err("survey (s,mu)/(s_perp,pi) counts need the sum of squares (x2sum)"); return FCFC_GPU_ERR_ARG; }
+  const T *s2bin = (const T *) b->s2bin, *pbin = (const T *) b->pbin;
+  const double s2min = s2bin[0], s2max = s2bin[ns];
+  const double pmin = np ? pbin[0] : 0, pmax = np ? pbin[np] : 0;
+  // table lengths: util/create_lut.c:62-64 (integer) and :105-107 (hybrid)
+  auto tablen = [&](const T *e, int n) -> long {
+    long mn = (long) e[0];
+    long mx = (b->tabtype == FCFC_GPU_TAB_INT) ? (long) e[n] : (long) std::ceil((double) e[n]);
+    return mx - mn;
+  };
+  const long nstab = b->nstab ? (long) b->nstab : tablen(s2bin, ns);
+  const long nptab = np ? (b->nptab ? (long) b->nptab : tablen(pbin, np)) : 0;
+  if (nstab <= 0 || nstab > (1 << 20) || nptab < 0 || nptab > (1 << 20)) { set_err("invalid lookup table length"); return FCFC_GPU_ERR_ARG; }
+
+  cudaEvent_t ev0, ev1, ev2, ev3;
+  cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2); cudaEventCreate(&ev3);
+  cudaEventRecord(ev0);
+  memset(&g_stats, 0, sizeof g_stats);
+
+  // ---- grid, cell lists, stencil ----
+  double lo[3], hi[3], maxabs = 0;
+  for (int d = 0; d < 3; d++) {
+    lo[d] = std::min(c1->bmin[d], c2->bmin[d]); hi[d] = std::max(c1->bmax[d], c2->bmax[d]);
+    maxabs = std::max(maxabs, std::max(std::fabs(lo[d]), std::fabs(hi[d])));
+    if (b->periodic) maxabs = std::max(maxabs, 2 * b->bsize[d]);
+  }
+  if (b->periodic) {
+    for (int d = 0; d < 3; d++) if (!(b->bsize[d] > 0)) { set_err("invalid box size"); return FCFC_GPU_ERR_ARG; }
+    const double rmax = std::sqrt(s2max);
+    for (int d = 0; d < 3; d++)
+      if (rmax >= 0.5 * b->bsize[d] || (bintype == BIN_SPI && pmax >= 0.5 * b->bsize[d])) {
+        set_err("the maximum separation must be smaller than half the box size"); return FCFC_GPU_ERR_ARG;
+      }
+  }
+  const Reach R = compute_reach(b, s2max, pmax, maxabs, std::max(c1->smax, c2->smax), is_float);
+  constexpr int RR = 4;
+  const int tile = 32 * RR;
+  const bool half = isauto != 0;
+  if (c1->n == 0 || c2->n == 0) {
+    if (withwt) { if (cnt_d) memset(cnt_d, 0, ntot * 8); } else if (cnt_i) memset(cnt_i, 0, ntot * 8);
+    if (dev_hist) cudaMemset(dev_hist, 0, ntot * 8);
+    return 0;
+  }
+  const Grid g = choose_grid(b, R, lo, hi, (double) c1->n, (double) c2->n, tile, half);
+  if (g.cs[0] <= 0) { set_err("failed to choose a cell grid"); return FCFC_GPU_ERR_TREE; }
+  float ms_sort = 0;
+  int e = build_sorted<T>(c1, g, tile, withwt != 0, &ms_sort);
+  if (e) return e;
+  if (c2 != c1) { e = build_sorted<T>(c2, g, tile, withwt != 0, &ms_sort); if (e) return e; }
+  Sorted<T> &S1 = sorted_of<T>(c1), &S2 = sorted_of<T>(c2);
+  std::vector<int4> rows = build_stencil(g, R, half);
+  if (rows.size() > (size_t) kMaxRows) { set_err("neighbour stencil too large (%zu rows)", rows.size()); return FCFC_GPU_ERR_TREE; }
+
+  // ---- device copies of the tables ----
+  const int sw = b->swidth ? 2 : 1, pw = b->pwidth ? 2 : 1;
+  const size_t sz_stab = (size_t) nstab * sw, sz_ptab = (size_t) nptab * pw, sz_mu = (bintype == BIN_SMU) ? (size_t) nmu * nmu : 0;
+  const size_t sz_s2 = (ns + 1) * sizeof(T), sz_pb = np ? (np + 1) * sizeof(T) : 0, sz_rows = rows.size() * sizeof(int4);
+  auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+  const size_t o_stab = 0, o_ptab = o_stab + al(sz_stab), o_mu = o_ptab + al(sz_ptab), o_s2 = o_mu + al(sz_mu),
+               o_pb = o_s2 + al(sz_s2), o_rows = o_pb + al(sz_pb), o_hist = o_rows + al(sz_rows),
+               o_cnt = o_hist + al(ntot * 8), o_end = o_cnt + 256;
+  std::vector<unsigned char> hbuf(o_end, 0);
+  memcpy(&hbuf[o_stab], b->stab, sz_stab);
+  if (sz_ptab) memcpy(&hbuf[o_ptab], b->ptab, sz_ptab);
+  if (sz_mu) memcpy(&hbuf[o_mu], b->mutab, sz_mu);
+  memcpy(&hbuf[o_s2], s2bin, sz_s2);
+  if (sz_pb) memcpy(&hbuf[o_pb], pbin, sz_pb);
+  if (sz_rows) memcpy(&hbuf[o_rows], rows.data(), sz_rows);
+  unsigned char *dbuf = nullptr;
+  CUDA_TRY(cudaMalloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(cudaMemcpy(dbuf, hbuf.data(), o_end, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+
+  // ---- kernel parameters ----
+  CountParams<T> P;
+  memset(&P, 0, sizeof P);
+  P.pos1 = S1.pos; P.w1 = S1.w; P.pos2 = S2.pos; P.w2 = S2.w; P.cell_start2 = S2.cell_start;
+  P.item_cell = S1.item_cell; P.item_off = S1.item_off; P.item_cnt = S1.item_cnt;
+  // shard: contiguous item ranges (cells are visited in memory order; cost balancing by item count)
+  const long long ni = S1.nitem;
+  P.item_begin = (int) (ni * part / nparts); P.item_end = (int) (ni * (part + 1) / nparts);
+  P.work_counter = reinterpret_cast<unsigned int *>(dbuf + o_cnt);
+  for (int d = 0; d < 3; d++) { P.nc[d] = g.nc[d]; P.bsize[d] = (T) b->bsize[d]; }
+  P.periodic = b->periodic;
+  P.rows = reinterpret_cast<const int4 *>(dbuf + o_rows); P.nrows = (int) rows.size();
+  P.s2min = (T) s2min; P.s2max = (T) s2max; P.pmin = (T) pmin; P.pmax = (T) pmax;
+  {
+    // survey (s_perp, pi): cheap pre-test s^2 < s2max + p2max before the division (see eval_pair)
+    double pm = (s2max + pmax) * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
+    P.premax = (T) pm; if ((double) P.premax < pm) P.premax = std::nextafter(P.premax, (T) INFINITY);
+  }
+  P.nmu2 = nmu * nmu; P.nmu2f = (T) (nmu * nmu);
+  P.ns = ns; P.np = np; P.ntot = (int) ntot;
+  P.soff = (int) s2bin[0]; P.poff = np ? (int) pbin[0] : 0;
+  P.tab_hybrid = (b->tabtype == FCFC_GPU_TAB_HYBRID); P.swidth = b->swidth; P.pwidth = b->pwidth;
+  P.with_mu_one = b->with_mu_one; P.smin0 = (s2bin[0] == 0); P.pmin0 = np ? (pbin[0] == 0) : 1;
+  P.stab = dbuf + o_stab; P.ptab = dbuf + o_ptab; P.mutab = dbuf + o_mu;
+  P.nstab = (int) nstab; P.nptab = (int) nptab;
+  P.s2bin = reinterpret_cast<const T *>(dbuf + o_s2); P.pbin = reinterpret_cast<const T *>(dbuf + o_pb);
+  P.isauto = isauto;
+  P.ghist_i = reinterpret_cast<unsigned long long *>(dbuf + o_hist);
+  P.ghist_d = reinterpret_cast<double *>(dbuf + o_hist);
+  P.gevals = reinterpret_cast<unsigned long long *>(dbuf + o_cnt + 8);
+
+  const bool generic = !(P.smin0 && P.pmin0 && !P.tab_hybrid && b->swidth == 0 && (np == 0 || b->pwidth == 0));
+  Variant v;
+  v.is_float = is_float; v.bintype = bintype; v.box = b->periodic != 0; v.wt = withwt != 0;
+  v.arith = b->arith ? 1 : 0; v.generic = generic;
+  // shared-memory budget decides whether the histogram lives in shared memory
+  int dev = 0; cudaGetDevice(&dev);
+  int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  const int nmutab = (bintype == BIN_SMU) ? nmu * nmu : 0;
+  SmemPlan pl = withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true)
+                       : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true);
+  v.smem_hist = pl.total + 1024 <= smem_max;
+  if (!v.smem_hist) {
+    pl = withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), false)
+                : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), false);
+    if (pl.total + 1024 > smem_max) { cudaFree(dbuf); set_err("lookup tables do not fit in shared memory (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  }
+  cudaEventRecord(ev1);
+  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + kWarpsPerBlock - 1) / kWarpsPerBlock));
+  cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
+  g_stats.kernel_launches++;
+  cudaEventRecord(ev2);
+  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); cudaFree(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  // ---- results ----
+  cudaError_t ce = cudaMemcpy(withwt ? (void *) cnt_d : (void *) cnt_i, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToHost);
+  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); cudaFree(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (dev_hist) cudaMemcpy(dev_hist, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToDevice);
+  unsigned long long ev = 0;
+  cudaMemcpy(&ev, dbuf + o_cnt + 8, 8, cudaMemcpyDeviceToHost);
+  cudaEventRecord(ev3); cudaEventSynchronize(ev3);
+  float ms_count = 0, ms_total = 0;
+  cudaEventElapsedTime(&ms_count, ev1, ev2); cudaEventElapsedTime(&ms_total, ev0, ev3);
+  g_stats.pair_evals = ev;
+  if (!withwt && cnt_i) { unsigned long long t = 0; for (size_t i = 0; i < ntot; i++) t += (unsigned long long) cnt_i[i]; g_stats.pairs_in = t; }
+  g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
+  for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];
+  g_stats.nitem = P.item_end - P.item_begin;
+  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
+  cudaFree(dbuf);
+  return 0;
+}
+
+}  // namespace fcfc
+
+// ==========================================================================================
+// C ABI
+using namespace fcfc;
+
+extern "C" int fcfc_gpu_abi_version(void) { return FCFC_GPU_ABI_VERSION; }
+extern "C" const char *fcfc_gpu_last_error(void) { return g_err.c_str(); }
+
+extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
+  g_verbose = verbose;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    set_err("no CUDA device available (%s); fcfc_b200 has no CPU fallback", e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    cudaGetLastError();
+    return FCFC_GPU_ERR_CUDA;
+  }
+  g_ctx.devices.clear();
+  if (ndev <= 0) ndev = devices ? 0 : count;
+  for (int i = 0; i < ndev; i++) {
+    int d = devices ? devices[i] : i;
+    if (d < 0 || d >= count) { set_err("invalid device %d", d); return FCFC_GPU_ERR_ARG; }
+    cudaDeviceProp p;
+    CUDA_TRY(cudaGetDeviceProperties(&p, d), FCFC_GPU_ERR_CUDA);
+    if (p.major != 10) { set_err("device %d (%s, sm_%d%d) is not a Blackwell sm_100 part", d, p.name, p.major, p.minor); return FCFC_GPU_ERR_CUDA; }
+    g_ctx.devices.push_back(d);
+    g_ctx.sm_count = p.multiProcessorCount;
+    if (verbose) fprintf(stderr, "[fcfc_gpu] device %d: %s, %d SMs\n", d, p.name, p.multiProcessorCount);
+  }
+  if (g_ctx.devices.empty()) { set_err("no device selected"); return FCFC_GPU_ERR_ARG; }
+  CUDA_TRY(cudaSetDevice(g_ctx.devices[0]), FCFC_GPU_ERR_CUDA);
+  g_ctx.ready = true;
+  return (int) g_ctx.devices.size();
+}
+
+extern "C" void fcfc_gpu_finalize(void) { g_ctx.ready = false; g_ctx.devices.clear(); }
+
+template <class T>
+static int catalog_upload(fcfc_gpu_catalog *c, const void *x, const void *y, const void *z, const void *s, const void *w,
+                          double rescale, int sumsq) {
+  const size_t n = c->n, bytes = (n ? n : 1) * sizeof(T);
+  CUDA_TRY(cudaMalloc(&c->x, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(cudaMalloc(&c->y, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(cudaMalloc(&c->z, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(cudaMemcpy(c->x, x, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  CUDA_TRY(cudaMemcpy(c->y, y, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  CUDA_TRY(cudaMemcpy(c->z, z, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  c->has_s = (s != nullptr) || sumsq >= 0;
+  if (c->has_s) {
+    CUDA_TRY(cudaMalloc(&c->s, bytes), FCFC_GPU_ERR_MEMORY);
+    if (s) CUDA_TRY(cudaMemcpy(c->s, s, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  }
+  c->has_w = w != nullptr;
+  if (w) {
+    CUDA_TRY(cudaMalloc(&c->w, bytes), FCFC_GPU_ERR_MEMORY);
+    CUDA_TRY(cudaMemcpy(c->w, w, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  }
+  unsigned long long *stats = nullptr; double *wsum = nullptr;
+  CUDA_TRY(cudaMalloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
+  wsum = reinterpret_cast<double *>(stats + 8);
+  unsigned long long init[9];
+  for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
+  init[6] = 0; init[7] = 0; init[8] = 0;
+  CUDA_TRY(cudaMemcpy(stats, init, sizeof init, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  if (n) {
+    const int nb = (int) std::min<size_t>((n + 255) / 256, 148 * 8);
+    prep_kernel<T><<<nb, 256>>>((T *) c->x, (T *) c->y, (T *) c->z, (T *) c->s, n, (T) rescale, rescale != 1.0,
+                                s ? -1 : sumsq, stats, wsum, (const T *) c->w);
+    g_stats.kernel_launches++;
+  }
+  unsigned long long out[9];
+  CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
+  cudaFree(stats);
+  if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
+  for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
+  c->smax = n ? dec_f64(out[6]) : 0;
+  double ws; memcpy(&ws, &out[8], 8);
+  c->wsum = w ? ws : (double) n;
+  return 0;
+}
+
+extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *y, const void *z, const void *x2sum,
+                                                     const void *w, size_t n, int is_float, double rescale, int sumsq_arith) {
+  if (ensure_init()) return nullptr;
+  if (n && (!x || !y || !z)) { set_err("NULL coordinate array"); return nullptr; }
+  if (n >= (1ull << 31) - 64) { set_err("catalogue too large for 32-bit point indices"); return nullptr; }
+  fcfc_gpu_catalog *c = new fcfc_gpu_catalog();
+  c->is_float = is_float; c->n = n; c->device = g_ctx.devices[0];
+  cudaSetDevice(c->device);
+  int e = is_float ? catalog_upload<float>(c, x, y, z, x2sum, w, rescale, sumsq_arith)
+                   : catalog_upload<double>(c, x, y, z, x2sum, w, rescale, sumsq_arith);
+  if (e) { fcfc_gpu_catalog_destroy(c); return nullptr; }
+  return c;
+}
+
+extern "C" void fcfc_gpu_catalog_destroy(fcfc_gpu_catalog *c) {
+  if (!c) return;
+  cudaFree(c->x); cudaFree(c->y); cudaFree(c->z); cudaFree(c->s); cudaFree(c->w);
+  c->sf.release(); c->sd.release();
+  delete c;
+}
+extern "C" size_t fcfc_gpu_catalog_size(const fcfc_gpu_catalog *c) { return c ? c->n : 0; }
+extern "C" double fcfc_gpu_catalog_wsum(const fcfc_gpu_catalog *c) { return c ? c->wsum : 0; }
+
+extern "C" int fcfc_gpu_count_partial(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto,
+                                      int withwt, int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
+  if (ensure_init()) return FCFC_GPU_ERR_CUDA;
+  if (!c1 || !c2 || !b) { set_err("NULL argument"); return FCFC_GPU_ERR_ARG; }
+  if ((withwt && !cnt_d) || (!withwt && !cnt_i)) { set_err("missing output array"); return FCFC_GPU_ERR_ARG; }
+  if (c1->is_float != c2->is_float || c1->is_float != (b->is_float != 0)) { set_err("precision mismatch between catalogues and bins"); return FCFC_GPU_ERR_ARG; }
+  if (nparts < 1 || part < 0 || part >= nparts) { set_err("invalid shard %d/%d", part, nparts); return FCFC_GPU_ERR_ARG; }
+  if (isauto && c1 != c2) { set_err("auto count needs cat1 == cat2"); return FCFC_GPU_ERR_ARG; }
+  if (withwt && (!c1->has_w && !c2->has_w)) { /* both unit weights: allowed, like the reference's w = 1 fill */ }
+  cudaSetDevice(c1->device);
+  return b->is_float ? count_impl<float>(c1, c2, b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist)
+                     : count_impl<double>(c1, c2, b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist);
+}
+
+extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
+                              int64_t *cnt_i, double *cnt_d) {
+  return fcfc_gpu_count_partial(c1, c2, b, isauto, withwt, 0, 1, cnt_i, cnt_d, nullptr);
+}
+
+extern "C" int fcfc_gpu_get_stats(fcfc_gpu_stats *out) {
+  if (!out) return FCFC_GPU_ERR_ARG;
+  *out = g_stats;
+  return 0;
+}

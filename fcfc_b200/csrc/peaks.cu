@@ -1,0 +1,47 @@
+// fcfc_b200/csrc/peaks.cu -- measured FP32 issue peak: the denominator of the pair-evaluation roofline.
+// MEASURED_PEAKS.json (driver-written) holds only HBM and BF16 tensor figures; the counting kernels
+// are bound by CUDA-core FP32 instruction issue, so the engine measures that
+// itself: independent FFMA chains, 8 per thread, all SMs, timed with CUDA events.
+#include "../../include/fcfc_gpu.h"
+#include <cuda_runtime.h>
+
+namespace {
+constexpr int kIters = 8192;
+__global__ void __launch_bounds__(1024) ffma_kernel(float *out, float a, float b) {
+  float x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-3f + i;
+  for (int it = 0; it < kIters; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = fmaf(x[i], a, b);
+  }
+  float s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+}  // namespace
+
+extern "C" double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  const int grid = p.multiProcessorCount * 2;
+  float *out = nullptr;
+  if (cudaMalloc(&out, sizeof(float) * grid * 1024) != cudaSuccess) return 0;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    ffma_kernel<<<grid, 1024>>>(out, 1.0001f, 0.5f);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = 0; break; }
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double) grid * 1024 * kIters * 8 / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  if (sm_clock_mhz_out) *sm_clock_mhz_out = best / (128.0 * p.multiProcessorCount) * 1e-6;  // implied clock at 128 lanes/SM
+  return best;
+}
