@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the pair-counting hot path (BASELINE.json).
+
+Workload (N=1): configs[1] of BASELINE.json -- FCFC_2PT_BOX xi(s, mu): 10^7 uniform points in a
+2 Gpc/h periodic box, s in [0, 200) Mpc/h in 40 bins x 120 mu bins, DD auto count.
+A "step" is one full count_pairs pass over that catalogue.
+
+  value    pair evaluations / s with the catalogue resident (cell-sorted) in HBM
+  e2e      same metric through the public C-ABI call sequence with HOST buffers:
+           catalog_create (H2D + rescale + cell sort) + count + histogram D2H, every step
+  roofline pair-evaluation roofline: FP32 issue peak (measured FFMA stream) / 6 instructions per evaluation
+  cpu_baseline / --impl reference: the unmodified reference (oracle/_ref, its fastest SIMD build, all host
+           cores) timed on count_pairs alone, on a bounded sample with the same number density and bins.
+           Its value is job-equivalent: (in-range pairs of the sample x evaluations-per-in-range-pair of this
+           workload) / seconds, so that the ratio of the two arms is the ratio of times for the same job.
+
+Multi-GPU (torchrun, one rank per GPU): the catalogue is replicated, the primary work items are split
+into WORLD_SIZE parts, and the per-rank histograms are combined by one NCCL all-reduce (strong scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (N, L, bintype, nmu)  -- s in [0,200) step 5 everywhere
+    "c2_box_smu_1e7": dict(n=10_000_000, box=2000.0, bintype=1, nmu=120, desc="FCFC_2PT_BOX xi(s,mu) 10^7 pts L=2000 40x120 bins DD"),
+    "c1_box_iso_1e6": dict(n=1_000_000, box=1000.0, bintype=0, nmu=1, desc="FCFC_2PT_BOX xi(s) 10^6 pts L=1000 40 bins DD"),
+}
+METRIC = "pair_evals_per_sec"
+UNIT = "pair evaluations/s"
+KAPPA_FILE = os.path.join(ROOT, "profiles", "workload_kappa.json")
+
+
+def make_box(n, L, seed=20261017):
+    rng = np.random.default_rng(seed)
+    return [np.ascontiguousarray(rng.random(n) * L) for _ in range(3)]
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index=0):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            self.path = tempfile.mktemp(suffix=".csv")
+            q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+                 "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if not self.proc:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            busy = [s for s in sm if s > 0.5 * max(sm)] or sm
+            out = {"sm_mhz": float(np.median(busy)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def run_reference_arm(args, wl, sample_n, prec):
+    """Time the unmodified reference (count_pairs only) on a bounded sample of the workload."""
+    from oracle import refdrv
+    dens = wl["n"] / wl["box"] ** 3
+    Ls = (sample_n / dens) ** (1.0 / 3.0)
+    cat = make_box(sample_n, Ls, seed=7)
+    flav = refdrv.best_simd_flavour("flt" if prec == "float" else "dbl")
+    p, isa = flav.split("_")
+    kw = dict(bintype=wl["bintype"], smin=0.0, smax=200.0, ds=5.0)
+    if wl["bintype"] == 1:
+        kw["nmu"] = wl["nmu"]
+    cores = os.cpu_count() or 1
+    pairs = 0
+    nrep = max(1, args.steps if args.impl == "reference" else 1)
+    warm = args.warmup if args.impl == "reference" else 0
+    times = []
+    for it in range(warm + nrep):
+        r = refdrv.run_reference([tuple(cat)], periodic=True, prec=p, isa=isa, pairs=["DD"], box=Ls, threads=cores, **kw)
+        if it >= warm:
+            times.append(r.pairs[0].t_count)
+        pairs = int(r.pairs[0].cnt.sum())
+    t = float(np.mean(times))
+    kappa = 3.0
+    try:
+        kappa = json.load(open(KAPPA_FILE)).get(args.workload, {}).get("evals_per_inrange_pair", kappa)
+    except Exception:
+        pass
+    return dict(seconds=t, pairs=pairs, value=kappa * pairs / t, kappa=kappa, cores=cores, flavour=flav,
+                sample=f"{sample_n} uniform points in a {Ls:.1f} Mpc/h box (same density and bins as the workload), "
+                       f"count_pairs only, reference build {flav}, OMP_NUM_THREADS={cores}, in-range pairs={pairs}, "
+                       f"{t:.3f} s; value = evals_per_inrange_pair({kappa:.3f}) x pairs / s")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2_box_smu_1e7", choices=sorted(WORKLOADS))
+    ap.add_argument("--prec", default="float", choices=["float", "double"])
+    ap.add_argument("--arith", type=int, default=1, help="0 scalar-parity order, 1 FMA order")
+    ap.add_argument("--cpu-sample", type=int, default=400_000, help="points of the bounded CPU sample")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    wl = WORKLOADS[args.workload]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    config = {"workload": f"{args.workload}: {wl['desc']}", "n_points": wl["n"], "box": wl["box"], "bins": f"40 s x {wl['nmu']} mu",
+              "arith": "fma" if args.arith else "scalar", "l2": "inputs (160 MB cell-sorted float4) larger than the 126 MB L2",
+              "parallelism": f"primary work items split over {world} rank(s), secondary replicated, NCCL all-reduce of the histogram"}
+
+    # ---------------------------------------------------------------- reference arm
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_reference_arm(args, wl, args.cpu_sample, args.prec)
+        line = {"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong",
+                "vs_baseline": None, "dtype": "f32" if args.prec == "float" else "f64", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+                "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "in_range_pairs_per_sec": r["pairs"] / r["seconds"]}
+        print(json.dumps(line))
+        return
+
+    # ---------------------------------------------------------------- our arm
+    import torch
+    import fcfc_b200 as F
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    F.init(devices=[local])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    bins = F.Bins(periodic=True, prec=args.prec, arith=args.arith, box=wl["box"], bintype=wl["bintype"], smin=0.0, smax=200.0,
+                  ds=5.0, nmu=wl["nmu"])
+    npdt = np.float32 if args.prec == "float" else np.float64
+    xyz = make_box(wl["n"], wl["box"])
+    # pinned host buffers of the build's `real` type (what the FCFC host holds after reading the catalogue)
+    pinned = [torch.from_numpy(a.astype(npdt)).pin_memory() for a in xyz]
+    host = [p.numpy() for p in pinned]
+    del xyz
+    ntot = bins.ntot
+    dev_hist = torch.zeros(ntot, dtype=torch.int64, device=dev)
+
+    cat = F.Catalog(*host, bins=bins)
+    launches = {"n": 0}
+    evals = {"n": 0}
+
+    def step_resident():
+        c = F.count_pairs(cat, None, bins, part=rank, nparts=world, dev_hist_ptr=dev_hist.data_ptr())
+        st = F.stats()
+        launches["n"] += st["kernel_launches"]; evals["n"] += st["pair_evals"]
+        if dist is not None:
+            dist.all_reduce(dev_hist)
+        return c, st
+
+    def step_e2e():
+        g = F.Catalog(*host, bins=bins)                       # H2D + rescale + stats
+        c = F.count_pairs(g, None, bins, part=rank, nparts=world, dev_hist_ptr=dev_hist.data_ptr())   # sort + count + D2H
+        st = F.stats()
+        if dist is not None:
+            dist.all_reduce(dev_hist)
+            c = dev_hist.cpu().numpy()
+        g.destroy()
+        return c, st
+
+    # ---- resident (value) ----
+    for _ in range(max(3, args.warmup)):
+        counts, st = step_resident()
+    launches["n"] = 0; evals["n"] = 0
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    kern_ms = []
+    for _ in range(args.steps):
+        counts, st = step_resident()
+        kern_ms.append(st["ms_count"])
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    ev = torch.tensor([float(evals["n"])], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ev, op=dist.ReduceOp.SUM)
+    ms = float(t_ms.item()); total_evals = float(ev.item())
+    value = total_evals / (ms * 1e-3)
+    total_counts = dev_hist.cpu().numpy() if dist is not None else counts
+    pairs_in = int(total_counts.sum())
+
+    # ---- end to end (host buffers, copies inside the timed region) ----
+    for _ in range(1):
+        step_e2e()
+    barrier()
+    e0.record()
+    ev_e2e = 0.0
+    for _ in range(args.steps):
+        c2, st2 = step_e2e()
+        ev_e2e += st2["pair_evals"]
+    e1.record()
+    barrier()
+    ms2 = e0.elapsed_time(e1)
+    t2 = torch.tensor([ms2], dtype=torch.float64, device=dev)
+    ev2 = torch.tensor([ev_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ev2, op=dist.ReduceOp.SUM)
+    e2e_value = float(ev2.item()) / (float(t2.item()) * 1e-3)
+    same = bool(np.array_equal(np.asarray(c2), total_counts))
+
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (count_kernel): FP32 issue peak / 6 instr per evaluation ----
+    peak_instr, implied_mhz = F.measure_fp32_peak()
+    k_ms = float(np.mean(kern_ms))
+    evals_per_launch = evals["n"] / args.steps
+    achieved = evals_per_launch / (k_ms * 1e-3) * 6.0 * 1e-12           # T FP32 lane-instructions/s of algorithmic work
+    roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peak_instr * 1e-12, "unit": "T FP32 instr/s (6 per pair evaluation)",
+                "frac": achieved / (peak_instr * 1e-12), "traffic": None, "kernel": "fcfc::count_kernel", "kernel_ms": k_ms,
+                "peak_source": "measured live: FFMA stream on all SMs (fcfc_gpu_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
+                "evals_per_sec_kernel": evals_per_launch / (k_ms * 1e-3), "r_eval_peak": peak_instr / 6.0}
+    kappa = evals["n"] / args.steps * world / max(pairs_in, 1) if world == 1 else total_evals / args.steps / max(pairs_in, 1)
+    try:
+        os.makedirs(os.path.dirname(KAPPA_FILE), exist_ok=True)
+        allk = json.load(open(KAPPA_FILE)) if os.path.exists(KAPPA_FILE) else {}
+        allk[args.workload] = {"evals_per_inrange_pair": kappa, "pairs_in": pairs_in}
+        json.dump(allk, open(KAPPA_FILE, "w"), indent=1)
+    except Exception:
+        pass
+
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            r = run_reference_arm(args, wl, args.cpu_sample, args.prec)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"],
+                   "in_range_pairs_per_sec": r["pairs"] / r["seconds"]}
+        except Exception as ex:     # the baseline is reported, never required for the product path
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+
+    bytes_in = 3 * wl["n"] * np.dtype(npdt).itemsize
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32" if args.prec == "float" else "f64", "data": "synthetic", "config": config, "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(bytes_in), "d2h_bytes_per_step": int(ntot * 8),
+                    "ms_per_step": float(t2.item()) / args.steps, "same_counts_as_resident": same},
+            "gpu_launches": int(launches["n"]), "roofline": roofline, "cpu_baseline": cpu,
+            "in_range_pairs": pairs_in, "in_range_pairs_per_sec": pairs_in / (ms / args.steps * 1e-3),
+            "evals_per_inrange_pair": kappa, "dd_wall_time_s": float(t2.item()) / args.steps * 1e-3,
+            "grid": st["ncell"], "work_items": st["nitem"]}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

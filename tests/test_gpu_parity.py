@@ -1,0 +1,257 @@
+"""GPU (-m gpu): the CUDA engine, called through the C ABI, against
+  (1) the golden vectors of the compiled reference (tests/golden),
+  (2) the brute-force CPU restatement (oracle/) on seeded inputs,
+  (3) the compiled reference itself run live on the host CPU (oracle/_ref travels to the GPU box),
+  (4) size-independent properties at BASELINE.json's full sizes.
+Bars: unweighted counts bit-exact; weighted FP64 sums within 1e-12 relative (north_star)."""
+import numpy as np
+import pytest
+
+from cases import CASES, box_catalog, clustered_box_catalog, lattice_box_catalog, make_catalog, survey_catalog
+from conftest import have_ref, load_golden
+from oracle import oracle, refdrv
+
+pytestmark = pytest.mark.gpu
+
+WT_RTOL = 1e-12
+
+
+def gpu_counts(F, case_kw, periodic, prec, cats, pairs, withwt, arith=0):
+    b = F.Bins(periodic=periodic, prec=prec, arith=arith, **case_kw)
+    g = [F.Catalog(*c, bins=b) for c in cats]
+    out = {}
+    for p in pairs:
+        i, j = "DR".index(p[0]), "DR".index(p[1])
+        out[p] = F.count_pairs(g[i], None if i == j else g[j], b, withwt=withwt)
+    for c in g:
+        c.destroy()
+    return out
+
+
+def assert_counts(got, want, withwt):
+    if withwt:
+        np.testing.assert_array_equal(got == 0, want == 0)
+        np.testing.assert_allclose(got, want, rtol=WT_RTOL, atol=0)
+    else:
+        np.testing.assert_array_equal(got, want)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("prec", ["dbl", "flt"])
+def test_golden_reference_vectors(gpu, name, prec):
+    case = CASES[name]
+    g = load_golden(name)
+    cats = [make_catalog(s, case["withwt"]) for s in case["cats"]]
+    got = gpu_counts(gpu, case["kw"], case["periodic"], "float" if prec == "flt" else "double", cats,
+                     case["pairs"], case["withwt"])
+    for p in case["pairs"]:
+        assert_counts(got[p], g[f"{prec}_scalar_{p}"], case["withwt"])
+        if prec == "dbl" and not case["withwt"]:
+            np.testing.assert_array_equal(got[p], g[f"dbl_avx512_{p}"])     # default (SIMD) build of the reference
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+@pytest.mark.parametrize("prec", ["double", "float"])
+@pytest.mark.parametrize("arith", [0, 1])
+def test_against_oracle(gpu, name, prec, arith):
+    """Both arithmetic orders (scalar parity mode, FMA mode) against the brute-force restatement."""
+    case = CASES[name]
+    cats = [make_catalog(s, case["withwt"]) for s in case["cats"]]
+    got = gpu_counts(gpu, case["kw"], case["periodic"], prec, cats, case["pairs"], case["withwt"], arith)
+    ob = oracle.setup(prec=prec[0], periodic=case["periodic"], arith=arith, **case["kw"])
+    pc = [oracle.preprocess(ob, c) for c in cats]
+    for p in case["pairs"]:
+        i, j = "DR".index(p[0]), "DR".index(p[1])
+        want = oracle.count(ob, pc[i], None if i == j else pc[j], withwt=case["withwt"])
+        assert_counts(got[p], want, case["withwt"])
+
+
+@pytest.mark.parametrize("prec", ["double", "float"])
+@pytest.mark.parametrize("kw", [dict(bintype=1, smax=40.0, ds=1.0, nmu=120), dict(bintype=0, smax=37.5, ds=2.5),
+                                dict(bintype=2, smax=30.0, ds=1.0, pmin=0.0, pmax=40.0, dpi=1.0)])
+def test_medium_box_vs_oracle(gpu, prec, kw):
+    """25k points in a small box: many cells, several tiles per cell, every periodic image exercised."""
+    cat = box_catalog(25000, 300.0, 31, weights=False)
+    got = gpu_counts(gpu, dict(box=300.0, **kw), True, prec, [cat], ["DD"], False)["DD"]
+    ob = oracle.setup(prec=prec[0], periodic=True, box=300.0, **kw)
+    np.testing.assert_array_equal(got, oracle.count(ob, oracle.preprocess(ob, cat)))
+
+
+@pytest.mark.parametrize("prec", ["double", "float"])
+def test_clustered_cuboid_vs_oracle(gpu, prec):
+    cat = clustered_box_catalog(20000, 400.0, 32)
+    x, y, z, w = cat
+    cat = (x, y * 0.75, z * 0.5, w)                     # cuboid box 400 x 300 x 200
+    kw = dict(box=[400.0, 300.0, 200.0], bintype=1, smax=30.0, ds=1.5, nmu=40)
+    for withwt in (False, True):
+        c = cat if withwt else cat[:3]
+        got = gpu_counts(gpu, kw, True, prec, [c], ["DD"], withwt)["DD"]
+        ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+        assert_counts(got, oracle.count(ob, oracle.preprocess(ob, c), withwt=withwt), withwt)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.skipif(not have_ref("dbl_scalar", "box"), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("kw", [dict(bintype=0, smax=200.0, ds=5.0), dict(bintype=1, smax=200.0, ds=5.0, nmu=120)])
+def test_live_reference_box_double(gpu, kw):
+    """2x10^5 points against the unmodified reference (its fastest build on this host), bit-exact."""
+    cat = box_catalog(200000, 1000.0, 41, weights=False)
+    flavour = refdrv.best_simd_flavour("dbl").split("_")[1]
+    r = refdrv.run_reference([cat], periodic=True, prec="dbl", isa=flavour, pairs=["DD"], box=1000.0, **kw)
+    got = gpu_counts(gpu, dict(box=1000.0, **kw), True, "double", [cat], ["DD"], False)["DD"]
+    np.testing.assert_array_equal(got, r.pairs[0].cnt)
+
+
+@pytest.mark.skipif(not have_ref("flt_scalar", "svy"), reason="oracle/_ref not shipped")
+@pytest.mark.parametrize("prec", ["dbl", "flt"])
+def test_live_reference_survey_weighted(gpu, prec):
+    """Survey mode never crosses a periodic boundary, so SINGLE_PREC is exact against the scalar reference too."""
+    D, R = survey_catalog(40000, 42), survey_catalog(120000, 43)
+    kw = dict(bintype=2, smax=40.0, ds=2.0, pmin=0.0, pmax=80.0, dpi=1.0)
+    r = refdrv.run_reference([D, R], periodic=False, prec=prec, isa="scalar", pairs=["DD", "DR", "RR"], **kw)
+    got = gpu_counts(gpu, kw, False, "float" if prec == "flt" else "double", [D, R], ["DD", "DR", "RR"], True)
+    for k, p in enumerate(["DD", "DR", "RR"]):
+        assert_counts(got[p], r.pairs[k].cnt, True)
+    r = refdrv.run_reference([D[:3], R[:3]], periodic=False, prec=prec, isa="scalar", pairs=["DD", "DR"], **kw)
+    got = gpu_counts(gpu, kw, False, "float" if prec == "flt" else "double", [D[:3], R[:3]], ["DD", "DR"], False)
+    for k, p in enumerate(["DD", "DR"]):
+        np.testing.assert_array_equal(got[p], r.pairs[k].cnt)
+
+
+@pytest.mark.skipif(not have_ref("flt_scalar", "box"), reason="oracle/_ref not shipped")
+def test_live_reference_box_float_spread(gpu):
+    """Gate G2: against the SINGLE_PREC reference on a generic periodic catalogue the per-bin difference must
+    stay within the reference's own k-d-tree vs ball-tree spread (which is reported, not hidden)."""
+    cat = box_catalog(200000, 1000.0, 44, weights=False)
+    kw = dict(bintype=0, smax=200.0, ds=5.0)
+    kd = refdrv.run_reference([cat], periodic=True, prec="flt", isa="scalar", pairs=["DD"], box=1000.0, data_struct=0, **kw).pairs[0].cnt
+    ball = refdrv.run_reference([cat], periodic=True, prec="flt", isa="scalar", pairs=["DD"], box=1000.0, data_struct=1, **kw).pairs[0].cnt
+    got = gpu_counts(gpu, dict(box=1000.0, **kw), True, "float", [cat], ["DD"], False)["DD"]
+    own = np.abs(kd - ball)
+    ours = np.abs(got - kd)
+    print("reference kd-vs-ball: max", own.max(), "sum", own.sum(), "| engine-vs-kd: max", ours.max(), "sum", ours.sum())
+    assert ours.max() <= max(4, 2 * own.max()) and ours.sum() <= max(16, 2 * own.sum())
+    assert abs(int(got.sum()) - int(kd.sum())) <= max(4, 2 * abs(int(kd.sum()) - int(ball.sum())))
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_edge_cases(gpu):
+    F = gpu
+    kw = dict(box=100.0, bintype=1, smax=20.0, ds=1.0, nmu=10)
+    for prec in ("double", "float"):
+        b = F.Bins(periodic=True, prec=prec, **kw)
+        ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+        empty = F.Catalog([], [], [], bins=b)
+        one = F.Catalog([5.0], [5.0], [5.0], bins=b)
+        assert F.count_pairs(empty, None, b).sum() == 0
+        assert F.count_pairs(one, None, b).sum() == 0
+        assert F.count_pairs(one, empty, b).sum() == 0
+        # coincident points: every distinct pair lands in bin 0 (d^2 < EPS -> mu index 0)
+        n = 70
+        same = F.Catalog([50.0] * n, [50.0] * n, [50.0] * n, bins=b)
+        c = F.count_pairs(same, None, b)
+        assert c[0] == n * (n - 1) // 2 and c.sum() == c[0]
+        # ragged sizes around the tile (128) and warp (32) boundaries, points on the box faces
+        for n in (2, 31, 33, 127, 128, 129, 257, 1000):
+            rng = np.random.default_rng(n)
+            x = rng.random((n, 3)) * 100.0
+            x[0] = [0.0, 0.0, 0.0]
+            x[1] = [100.0, 100.0, 100.0] if prec == "float" else [99.999999, 0.0, 50.0]
+            cat = (x[:, 0], x[:, 1], x[:, 2])
+            g = F.Catalog(*cat, bins=b)
+            np.testing.assert_array_equal(F.count_pairs(g, None, b), oracle.count(ob, oracle.preprocess(ob, cat)))
+            np.testing.assert_array_equal(F.count_pairs(g, one, b),
+                                          oracle.count(ob, oracle.preprocess(ob, cat), oracle.preprocess(ob, ([5.0], [5.0], [5.0]))))
+
+
+def test_huge_histogram_uses_global_path(gpu):
+    """ns = 600 x nmu = 255 = 153000 bins do not fit the shared-memory histogram: global-atomic variant."""
+    kw = dict(box=500.0, bintype=1, smax=60.0, ds=0.1, nmu=255)
+    cat = box_catalog(6000, 500.0, 51, weights=False)
+    for prec in ("double", "float"):
+        got = gpu_counts(gpu, kw, True, prec, [cat], ["DD"], False)["DD"]
+        ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+        np.testing.assert_array_equal(got, oracle.count(ob, oracle.preprocess(ob, cat)))
+
+
+def test_with_mu_one(gpu):
+    kw = dict(box=200.0, bintype=1, smax=40.0, ds=2.0, nmu=20, with_mu_one=True)
+    x, y, z, _ = lattice_box_catalog(3000, 200.0, 52)     # lattice: many pairs exactly along z (mu = 1)
+    for prec in ("double", "float"):
+        got = gpu_counts(gpu, kw, True, prec, [(x, y, z)], ["DD"], False)["DD"]
+        ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+        np.testing.assert_array_equal(got, oracle.count(ob, oracle.preprocess(ob, (x, y, z))))
+        kw0 = dict(kw, with_mu_one=False)
+        got0 = gpu_counts(gpu, kw0, True, prec, [(x, y, z)], ["DD"], False)["DD"]
+        assert got0.sum() < got.sum()
+
+
+def test_errors(gpu):
+    F = gpu
+    b = F.Bins(periodic=True, prec="double", box=100.0, bintype=0, smax=20.0, ds=1.0)
+    bad = F.Catalog([1.0, 120.0], [1.0, 2.0], [1.0, 2.0], bins=b)
+    with pytest.raises(F.FcfcGpuError, match="outside the periodic box") as e:
+        F.count_pairs(bad, None, b)
+    assert e.value.code == -21
+    bf = F.Bins(periodic=True, prec="float", box=100.0, bintype=0, smax=20.0, ds=1.0)
+    with pytest.raises(F.FcfcGpuError, match="precision mismatch"):
+        F.count_pairs(bad, None, bf)
+    with pytest.raises(F.FcfcGpuError, match="non-finite"):
+        F.Catalog([1.0, float("nan")], [1.0, 2.0], [1.0, 2.0], bins=b)
+    with pytest.raises(F.FcfcGpuError, match="half the box"):
+        F.count_pairs(F.Catalog([1.0], [1.0], [1.0], bins=b), None,
+                      F.Bins(periodic=True, prec="double", box=30.0, bintype=0, smax=20.0, ds=1.0))
+
+
+# ---------------------------------------------------------------------------------------------------
+# Properties at BASELINE.json sizes (no brute force possible)
+@pytest.fixture(scope="module")
+def million():
+    return box_catalog(1000000, 1000.0, 61, weights=False)
+
+
+def test_full_size_properties_c1(gpu, million):
+    """configs[0]: 10^6 points, L = 1000, s in [0, 200) in 40 bins."""
+    F = gpu
+    for prec in ("float", "double"):
+        biso = F.Bins(periodic=True, prec=prec, box=1000.0, bintype=0, smax=200.0, ds=5.0)
+        bsmu = F.Bins(periodic=True, prec=prec, box=1000.0, bintype=1, smax=200.0, ds=5.0, nmu=120, with_mu_one=True)
+        g = F.Catalog(*million, bins=biso)
+        iso = F.count_pairs(g, None, biso)
+        st = F.stats()
+        # idempotence
+        np.testing.assert_array_equal(iso, F.count_pairs(g, None, biso))
+        # shards add up (the multi-GPU decomposition), any number of parts
+        for nparts in (2, 3, 8):
+            tot = sum(F.count_pairs(g, None, biso, part=p, nparts=nparts) for p in range(nparts))
+            np.testing.assert_array_equal(tot, iso)
+        # (s, mu) with mu = 1 kept, summed over mu, is the isotropic count
+        smu = F.count_pairs(g, None, bsmu)
+        np.testing.assert_array_equal(smu.reshape(120, 40).sum(axis=0), iso)
+        # cross count of a catalogue with a copy of itself = ordered pairs + the N self pairs in bin 0
+        g2 = F.Catalog(*million, bins=biso)
+        cross = F.count_pairs(g, g2, biso)
+        want = 2 * iso
+        want[0] += len(million[0])
+        np.testing.assert_array_equal(cross, want)
+        # expected number of pairs for a uniform field (4/3 pi r^3 n^2 / 2), 5 sigma
+        n = len(million[0])
+        expect = 0.5 * n * (n - 1) * (4.0 / 3.0 * np.pi * 200.0 ** 3) / 1000.0 ** 3
+        assert abs(iso.sum() - expect) < 5 * np.sqrt(expect) + 1e-4 * expect
+        assert st["pair_evals"] >= iso.sum()
+        g.destroy(); g2.destroy()
+
+
+def test_full_size_lattice_float_equals_double(gpu):
+    """10^6 lattice points, power-of-two bins: every float operation is exact, so float == double exactly,
+    in both arithmetic orders (gate G2's dyadic-grid check at full size)."""
+    F = gpu
+    cat = lattice_box_catalog(1000000, 1024.0, 62)[:3]
+    kw = dict(box=1024.0, bintype=2, smax=128.0, ds=8.0, pmin=0.0, pmax=128.0, dpi=8.0)
+    res = []
+    for prec in ("double", "float"):
+        for arith in (0, 1):
+            res.append(gpu_counts(F, kw, True, prec, [cat], ["DD"], False, arith)["DD"])
+    for r in res[1:]:
+        np.testing.assert_array_equal(r, res[0])
