@@ -15,9 +15,13 @@
 //     private shared-memory buffer (coalesced 128-bit loads, periodic shift applied while
 //     staging) and every lane reads them back with broadcast LDS.128;
 //   * per pair: 3 subtractions + 1 multiply + 2 FMA (6 FP32 instructions, FMA mode) or
-//     3 sub + 3 mul + 2 add (scalar-parity mode), one compare; accepted pairs go through the
-//     reference's lookup tables into a per-block shared-memory histogram (32-bit counters,
-//     flushed lock-free to 64-bit global counters; FP64 sums for weighted counts).
+//     3 sub + 3 mul + 2 add (scalar-parity mode) and one compare.  Pairs that pass the range test
+//     are NOT binned in place (that would leave most lanes idle in a divergent branch): each lane
+//     appends (d^2, aux[, w]) to its own circular queue in shared memory (one predicated store);
+//   * when a queue is nearly full the warp drains: every lane pops its own entries, so all 32
+//     lanes run the expensive part (division for mu, table lookups, shared-memory atomic) together;
+//     the histogram is per block in shared memory (32-bit counters flushed lock-free to 64-bit
+//     global counters; FP64 sums for weighted counts).
 //
 // No tensor cores: the work is FP32/FP64 CUDA-core arithmetic plus shared-memory atomics.
 #pragma once
@@ -87,11 +91,14 @@ template <class T> struct CountParams {
   // binning
   T s2min, s2max, pmin, pmax, premax, nmu2f;
   int ns, np, nmu2, ntot, soff, poff;
-  int tab_hybrid, swidth, pwidth, with_mu_one, smin0, pmin0, mu_is_sqrt;
+  int tab_hybrid, swidth, pwidth, with_mu_one, smin0, pmin0;
+  int mu_is_sqrt, stab_is_sqrt, ptab_is_ident;     // tables that equal floor(sqrt(i)) / i are computed, not looked up
   const uint8_t *stab; const uint8_t *ptab; const uint8_t *mutab;
   int nstab, nptab;                     // entries
   const T *s2bin; const T *pbin;
   int isauto;
+  int tabs_global;                      // lookup tables too large for shared memory: read them from global memory
+  int qdepth;                           // entries per lane of the accepted-pair queues (power of two)
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
   unsigned long long *gevals;           // [0] candidate pair evaluations
@@ -99,25 +106,34 @@ template <class T> struct CountParams {
 
 // Shared-memory plan (dynamic): [hist][tables][edges][rows][per-warp staging]
 struct SmemPlan {
-  int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_stage, stage_per_warp, total;
+  int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_misc, off_stage, stage_per_warp, off_queue, queue_per_warp, total;
+};
+
+// Words of `real` per queue entry: ISO d2[,w]; box (s,mu)/(s_perp,pi) d2,aux[,w]; survey t,s1,s2[,w].
+template <int BIN, bool BOX, bool WT> struct QFmt {
+  static constexpr int NW = (BIN == BIN_ISO) ? (WT ? 2 : 1) : (BOX ? (WT ? 4 : 2) : 4);
 };
 
 template <class T, bool WT>
 __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, int nptab_bytes, int nmutab_bytes,
-                                                   int ns, int np, int nrows, bool smem_hist) {
+                                                   int ns, int np, int nrows, bool smem_hist, int qwords, int qdepth, bool tabs_global) {
   SmemPlan p;
   int o = 0;
   auto al = [](int v) { return (v + 15) & ~15; };
   p.off_hist = o; o += smem_hist ? al(ntot * (WT ? 8 : 4)) : 0;
-  p.off_stab = o; o += al(nstab_bytes);
-  p.off_ptab = o; o += al(nptab_bytes);
-  p.off_mutab = o; o += al(nmutab_bytes);
+  p.off_stab = o; o += tabs_global ? 0 : al(nstab_bytes);
+  p.off_ptab = o; o += tabs_global ? 0 : al(nptab_bytes);
+  p.off_mutab = o; o += tabs_global ? 0 : al(nmutab_bytes);
   p.off_s2bin = o; o += al((ns + 1) * (int) sizeof(T));
   p.off_pbin = o; o += al((np + 1) * (int) sizeof(T));
   p.off_rows = o; o += al(nrows * 16);
+  p.off_misc = o; o += 16;                      // overflow counter of the 32-bit histogram
   p.off_stage = o;
   p.stage_per_warp = 32 * (int) sizeof(Vec4<T>) + (WT ? 32 * (int) sizeof(T) : 0);
   o += kWarpsPerBlock * p.stage_per_warp;
+  p.off_queue = o;
+  p.queue_per_warp = qdepth * 32 * qwords * (int) sizeof(T);
+  o += (kWarpsPerBlock + 1) * p.queue_per_warp;       // + one queue of slack: the region is aligned at run time
   p.total = o;
   return p;
 }
@@ -226,10 +242,9 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
 }
 
 template <class T, bool WT, bool SMEMHIST>
-__device__ __forceinline__ void hist_add(const BlockCtx<T> &C, int bin, T wa, T wb) {
+__device__ __forceinline__ void hist_add(const BlockCtx<T> &C, int bin, T w) {
   if (WT) {
-    T w = Ar<T>::mul(wa, wb);                   // product in `real`, sum in double: metric_common.c:216-231
-    atomicAdd(&C.hist_d[bin], (double) w);
+    atomicAdd(&C.hist_d[bin], (double) w);      // product formed in `real`, summed in double: metric_common.c:216-231
   } else if (SMEMHIST) {
     atomicAdd(&C.hist_u[bin], 1u);
   } else {
@@ -246,14 +261,170 @@ __device__ __forceinline__ void sweep_hist(unsigned int *h, unsigned long long *
   }
 }
 
-// One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane.
-template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int R, bool SELF>
-__device__ __forceinline__ void do_chunk(const CountParams<T> &P, const BlockCtx<T> &C,
-                                         const Vec4<T> *sbuf, const T *wbuf, int nj,
-                                         const T (&ax)[R], const T (&ay)[R], const T (&az)[R], const T (&as)[R],
-                                         const T (&aw)[R], int jglob0, int iglob0) {
+// ---------------------------------------------------------------------------------------------
+// Per-lane circular queues of accepted pairs, addressed with 32-bit shared-window addresses.
+// Layout: [slot][lane][NW words]; a warp-wide push or pop touches 32 consecutive entries (no bank
+// conflicts).  The queue of a warp is aligned to its own size so that advancing a pointer is
+// ptr = (ptr & ~amask) | ((ptr + stride) & amask): one add and one LOP3.
+template <class T, int NW> struct QOps;
+template <int NW> struct QOps<float, NW> {
+  static __device__ __forceinline__ void store(unsigned a, const float (&v)[NW], bool p) {
+    if (NW == 1) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f32 [%1], %2;}" ::"r"((int) p), "r"(a), "f"(v[0]) : "memory");
+    else if (NW == 2) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f32 [%1], {%2, %3};}" ::"r"((int) p), "r"(a), "f"(v[0]), "f"(v[1 % NW]) : "memory");
+    else asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v4.f32 [%1], {%2, %3, %4, %5};}" ::"r"((int) p), "r"(a), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]) : "memory");
+  }
+  static __device__ __forceinline__ void load(unsigned a, float (&v)[NW]) {
+    if (NW == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a) : "memory");
+    else if (NW == 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1 % NW]) : "r"(a) : "memory");
+    else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1 % NW]), "=f"(v[2 % NW]), "=f"(v[3 % NW]) : "r"(a) : "memory");
+  }
+};
+template <int NW> struct QOps<double, NW> {
+  static __device__ __forceinline__ void store(unsigned a, const double (&v)[NW], bool p) {
+    if (NW == 1) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f64 [%1], %2;}" ::"r"((int) p), "r"(a), "d"(v[0]) : "memory");
+    else {
+      asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3};}" ::"r"((int) p), "r"(a), "d"(v[0]), "d"(v[1 % NW]) : "memory");
+      if (NW == 4) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f64 [%1+16], {%2, %3};}" ::"r"((int) p), "r"(a), "d"(v[2 % NW]), "d"(v[3 % NW]) : "memory");
+    }
+  }
+  static __device__ __forceinline__ void load(unsigned a, double (&v)[NW]) {
+    if (NW == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a) : "memory");
+    else {
+      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1 % NW]) : "r"(a) : "memory");
+      if (NW == 4) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v[2 % NW]), "=d"(v[3 % NW]) : "r"(a) : "memory");
+    }
+  }
+};
+
+template <class T, int NW> struct LaneQueue {
+  unsigned int wptr, rptr;      // shared addresses of the next free slot / the oldest entry (this lane's column)
+  unsigned int amask;           // queue bytes per warp - 1
+  static constexpr unsigned int kStride = 32u * NW * sizeof(T);
+  __device__ __forceinline__ unsigned int next(unsigned int p) const { return (p & ~amask) | ((p + kStride) & amask); }
+  __device__ __forceinline__ void push(const T (&v)[NW], bool ok) {
+    QOps<T, NW>::store(wptr, v, ok);
+    const unsigned int n = next(wptr);
+    wptr = ok ? n : wptr;
+  }
+  __device__ __forceinline__ unsigned int fill_bytes() const { return (wptr - rptr) & amask; }
+};
+
+// Truncation of 0 <= x < 2^23 (float) / 2^31 (double) without the quarter-rate F2I: add 2^23 (2^52)
+// rounding toward zero and read the low mantissa bits.
+__device__ __forceinline__ int trunc_pos(float x) { return __float_as_int(__fadd_rz(x, 8388608.0f)) - 0x4B000000; }
+__device__ __forceinline__ int trunc_pos(double x) { return __double2loint(__dadd_rz(x, 4503599627370496.0)); }
+// floor(sqrt(m)) for an integer 0 <= m < 2^18: sqrt(m + 1/2) is at least 0.25/sqrt(m) away from every
+// integer, far more than the error of the approximate square root.
+__device__ __forceinline__ int isqrt_small(int m) {
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"((float) m + 0.5f));
+  return trunc_pos(r);
+}
+// Quotient rounded toward zero for a >= 0, b > 0: the residual of the round-to-nearest quotient is exact.
+__device__ __forceinline__ float div_rz_pos(float a, float b) {
+  float q = __fdiv_rn(a, b);
+  return (__fmaf_rn(-q, b, a) < 0.0f) ? __int_as_float(__float_as_int(q) - 1) : q;
+}
+__device__ __forceinline__ double div_rz_pos(double a, double b) {
+  double q = __ddiv_rn(a, b);
+  return (__fma_rn(-q, b, a) < 0.0) ? __longlong_as_double(__double_as_longlong(q) - 1) : q;
+}
+
+// Histogram bin of one queued pair, -1 if it is dropped after all.  The fast variant (GENERIC = false:
+// zero lower bounds, 8-bit integer tables in shared memory) is branch-free for box / isotropic counts;
+// everything else goes through finish_pair.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, int NW>
+__device__ __forceinline__ int bin_entry(const CountParams<T> &P, const BlockCtx<T> &C, const T (&e)[NW], T &w) {
+  using A = Ar<T>;
+  w = (T) 1;
+  if (!GENERIC && (BOX || BIN == BIN_ISO)) {
+    const T d2 = e[0];
+    if (WT) w = e[(BIN == BIN_ISO) ? 1 % NW : 2 % NW];
+    const int si = trunc_pos(d2);
+    int sb;
+    if (P.stab_is_sqrt) sb = isqrt_small(si); else sb = C.stab[si];
+    int pb = 0;
+    bool ok = true;
+    if (BIN == BIN_SMU) {
+      const T dz2 = e[1 % NW];
+      int m;
+      if (ARITH == ARITH_SCALAR) {              // metric_common.c:184
+        m = trunc_pos(A::mul(A::div(dz2, d2), P.nmu2f));
+        m = (d2 < A::eps()) ? 0 : m;
+      } else {                                  // metric_common.c:472-494 (AVX-512 branch)
+        const T q = div_rz_pos(A::mul(dz2, P.nmu2f), d2);
+        m = (q < P.nmu2f) ? trunc_pos(q) : P.nmu2;
+        m = (d2 >= A::eps()) ? m : 0;
+      }
+      if (m >= P.nmu2) { ok = P.with_mu_one != 0; m = P.nmu2 - 1; }
+      if (P.mu_is_sqrt) pb = isqrt_small(m); else pb = C.mutab[m];
+    } else if (BIN == BIN_SPI) {
+      const int pi_i = trunc_pos(e[1 % NW]);
+      if (P.ptab_is_ident) pb = pi_i; else pb = C.ptab[pi_i];
+    }
+    return ok ? sb + pb * P.ns : -1;
+  } else {
+    T d2, aux = 0, as = 0, bs = 0;
+    if (BIN == BIN_ISO) { d2 = e[0]; if (WT) w = e[1 % NW]; }
+    else if (BOX) { d2 = e[0]; aux = e[1 % NW]; if (WT) w = e[2 % NW]; }
+    else {      // survey: rebuild s^2 = (s1 + s2) - t with the same two operations as eval_pair
+      aux = e[0]; as = e[1 % NW]; bs = e[2 % NW]; if (WT) w = e[3 % NW];
+      d2 = A::sub(A::add(as, bs), aux);
+    }
+    return finish_pair<T, BIN, BOX, ARITH, GENERIC>(P, C, d2, aux, as, bs);
+  }
+}
+
+// Pop and bin entries.  Called when the fullest queue may overflow: if it really is close to full,
+// `rounds` entries are popped from every lane (two per iteration for instruction-level parallelism);
+// lanes that run dry simply idle.  Returns the new upper bound of the fullest queue (entries).
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int NW>
+__device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockCtx<T> &C, LaneQueue<T, NW> &Q, int need, int keep) {
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  const int mx = (int) (__reduce_max_sync(0xffffffffu, Q.fill_bytes()) / S);
+  if (mx + need <= P.qdepth - 1) return mx;
+  const int rounds = mx - keep;
+#pragma unroll 1
+  for (int k = 0; k < rounds; k += 2) {
+    const unsigned int fill = Q.fill_bytes();
+    const bool h0 = fill != 0, h1 = fill > S;
+    const unsigned int p0 = Q.rptr, p1 = Q.next(p0);
+    T e0[NW], e1[NW];
+    QOps<T, NW>::load(p0, e0);
+    QOps<T, NW>::load(p1, e1);
+    Q.rptr = h1 ? Q.next(p1) : (h0 ? p1 : p0);
+    T w0 = 0, w1 = 0;
+    int b0 = -1, b1 = -1;
+    if (!GENERIC && (BOX || BIN == BIN_ISO)) {
+      // branch-free: slots past the tail hold stale data, zero them so that every table index stays in range
+#pragma unroll
+      for (int i = 0; i < NW; i++) { e0[i] = h0 ? e0[i] : (T) 0; e1[i] = h1 ? e1[i] : (T) 0; }
+      b0 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e0, w0);
+      b1 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e1, w1);
+    } else {
+      if (h0) b0 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e0, w0);
+      if (h1) b1 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e1, w1);
+    }
+    if (h0 && b0 >= 0) hist_add<T, WT, SMEMHIST>(C, b0, w0);
+    if (h1 && b1 >= 0) hist_add<T, WT, SMEMHIST>(C, b1, w1);
+  }
+  return max(keep, 0);
+}
+
+// One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane,
+// starting at staged point j0.  Returns nj when the chunk is done, or the index of the point at which
+// the queues must be drained first (the caller drains at its single call site and resumes).
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, int R, bool SELF, int NW, int RMAX>
+__device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW> &Q, int &ub,
+                                        const Vec4<T> *sbuf, const T *wbuf, int j0, int nj,
+                                        const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX], const T (&as)[RMAX],
+                                        const T (&aw)[RMAX], int jglob0, int iglob0) {
+  const int room = P.qdepth - 1 - R;            // `ub` (warp-uniform bound of the fullest queue) must stay <= room
+  int j = j0;
 #pragma unroll 2
-  for (int j = 0; j < nj; j++) {
+  for (; j < nj; j++) {
+    if (ub > room) break;
+    ub += R;
     const Vec4<T> b = sbuf[j];
     T bw = (T) 1;
     if (WT) bw = wbuf[j];
@@ -262,22 +433,24 @@ __device__ __forceinline__ void do_chunk(const CountParams<T> &P, const BlockCtx
       T d2, aux;
       bool ok = eval_pair<T, BIN, BOX, ARITH, GENERIC>(P, ax[r], ay[r], az[r], as[r], b, d2, aux);
       if (SELF) ok = ok && (jglob0 + j > iglob0 + r * 32);      // unordered pairs once: metric_common.c:2017-2018
-      if (ok) {
-        int bin = finish_pair<T, BIN, BOX, ARITH, GENERIC>(P, C, d2, aux, as[r], b.s);
-        if (bin >= 0) hist_add<T, WT, SMEMHIST>(C, bin, aw[r], bw);
-      }
+      T e[NW];
+      if (BIN == BIN_ISO) { e[0] = d2; if (WT) e[1 % NW] = Ar<T>::mul(aw[r], bw); }
+      else if (BOX) { e[0] = d2; e[1 % NW] = aux; if (WT) { e[2 % NW] = Ar<T>::mul(aw[r], bw); e[3 % NW] = 0; } }
+      else { e[0] = aux; e[1 % NW] = as[r]; e[2 % NW] = b.s; e[3 % NW] = WT ? Ar<T>::mul(aw[r], bw) : (T) 0; }
+      Q.push(e, ok);
     }
   }
+  return j;
 }
 
-template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int R>
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int RMAX>
 __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  __shared__ unsigned int s_blk_evals;
+  constexpr int NW = QFmt<BIN, BOX, WT>::NW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
   const SmemPlan pl = make_smem_plan<T, WT>(P.ntot, P.nstab * (P.swidth ? 2 : 1), P.nptab * (P.pwidth ? 2 : 1),
-                                            nmutab, P.ns, P.np, P.nrows, SMEMHIST);
+                                            nmutab, P.ns, P.np, P.nrows, SMEMHIST, NW, P.qdepth, P.tabs_global != 0);
   BlockCtx<T> C;
   C.hist_u = SMEMHIST ? reinterpret_cast<unsigned int *>(smem + pl.off_hist) : reinterpret_cast<unsigned int *>(P.ghist_i);
   C.hist_d = SMEMHIST ? reinterpret_cast<double *>(smem + pl.off_hist) : P.ghist_d;
@@ -285,24 +458,37 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
   T *s_s2bin = reinterpret_cast<T *>(smem + pl.off_s2bin), *s_pbin = reinterpret_cast<T *>(smem + pl.off_pbin);
   int4 *s_rows = reinterpret_cast<int4 *>(smem + pl.off_rows);
   C.stab = s_stab; C.ptab = s_ptab; C.mutab = s_mutab; C.s2bin = s_s2bin; C.pbin = s_pbin;
-  C.blk_evals = &s_blk_evals;
+  if (GENERIC && P.tabs_global) { C.stab = P.stab; C.ptab = P.ptab; C.mutab = P.mutab; }     // generic variant only
+  unsigned int *s_blk_evals = reinterpret_cast<unsigned int *>(smem + pl.off_misc);
+  C.blk_evals = s_blk_evals;
 
   // ---- block prologue: zero the histogram, stage tables / edges / stencil rows ----
   if (SMEMHIST) {
     if (WT) for (int i = threadIdx.x; i < P.ntot; i += kThreads) C.hist_d[i] = 0.0;
     else for (int i = threadIdx.x; i < P.ntot; i += kThreads) C.hist_u[i] = 0u;
   }
-  for (int i = threadIdx.x; i < P.nstab * (P.swidth ? 2 : 1); i += kThreads) s_stab[i] = P.stab[i];
-  if (BIN == BIN_SPI) for (int i = threadIdx.x; i < P.nptab * (P.pwidth ? 2 : 1); i += kThreads) s_ptab[i] = P.ptab[i];
-  if (BIN == BIN_SMU) for (int i = threadIdx.x; i < nmutab; i += kThreads) s_mutab[i] = P.mutab[i];
+  if (!P.tabs_global) {
+    for (int i = threadIdx.x; i < P.nstab * (P.swidth ? 2 : 1); i += kThreads) s_stab[i] = P.stab[i];
+    if (BIN == BIN_SPI) for (int i = threadIdx.x; i < P.nptab * (P.pwidth ? 2 : 1); i += kThreads) s_ptab[i] = P.ptab[i];
+    if (BIN == BIN_SMU) for (int i = threadIdx.x; i < nmutab; i += kThreads) s_mutab[i] = P.mutab[i];
+  }
   for (int i = threadIdx.x; i <= P.ns; i += kThreads) s_s2bin[i] = P.s2bin[i];
   if (BIN == BIN_SPI) for (int i = threadIdx.x; i <= P.np; i += kThreads) s_pbin[i] = P.pbin[i];
   for (int i = threadIdx.x; i < P.nrows; i += kThreads) s_rows[i] = P.rows[i];
-  if (threadIdx.x == 0) s_blk_evals = 0;
+  if (threadIdx.x == 0) *s_blk_evals = 0;
   __syncthreads();
 
   Vec4<T> *sbuf = reinterpret_cast<Vec4<T> *>(smem + pl.off_stage + warp * pl.stage_per_warp);
   T *wbuf = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sbuf) + 32 * sizeof(Vec4<T>));
+  LaneQueue<T, NW> Q;
+  {
+    const unsigned int qbytes = (unsigned int) pl.queue_per_warp;
+    unsigned int qbase = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue);
+    qbase = (qbase + qbytes - 1) & ~(qbytes - 1);               // align to the queue size (slack reserved in the plan)
+    Q.amask = qbytes - 1;
+    Q.wptr = Q.rptr = qbase + warp * qbytes + lane * (unsigned int) (NW * sizeof(T));
+  }
+  int ub = 0;                   // warp-uniform upper bound of the fullest lane queue (entries)
   unsigned long long my_evals = 0;
   const int ncy = P.nc[1], ncz = P.nc[2];
 
@@ -314,11 +500,12 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
     if (item >= P.item_end) break;
     const int cell = P.item_cell[item], t0 = P.item_off[item], cnt = P.item_cnt[item];
     const int iz = cell % ncz, iy = (cell / ncz) % ncy, ix = cell / (ncz * ncy);
+    const int nr = (cnt + 31) >> 5;             // primaries per lane actually used by this tile (1..RMAX)
 
     // primaries: lane holds points t0 + r*32 + lane; padding lanes sit far away (never in range)
-    T px[R], py[R], pz[R], ps[R], pw[R];
+    T px[RMAX], py[RMAX], pz[RMAX], ps[RMAX], pw[RMAX];
 #pragma unroll
-    for (int r = 0; r < R; r++) {
+    for (int r = 0; r < RMAX; r++) {
       const int k = r * 32 + lane;
       if (k < cnt) {
         Vec4<T> v = P.pos1[t0 + k];
@@ -334,9 +521,9 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
     // One contiguous range [b, e) of secondary points with per-axis image shifts.
     // sa: shift added to the primaries, sb: shift added to the secondaries (the lower point gets +L).
     auto sweep_range = [&](int b, int e, T sax, T say, T saz, T sbx, T sby, T sbz, bool self) {
-      T ax[R], ay[R], az[R];
+      T ax[RMAX], ay[RMAX], az[RMAX];
 #pragma unroll
-      for (int r = 0; r < R; r++) {
+      for (int r = 0; r < RMAX; r++) {
         ax[r] = BOX ? Ar<T>::add(px[r], sax) : px[r];
         ay[r] = BOX ? Ar<T>::add(py[r], say) : py[r];
         az[r] = BOX ? Ar<T>::add(pz[r], saz) : pz[r];
@@ -371,10 +558,23 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
           jn = c0 + 32 + lane;
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
-          if (self && c0 < t0 + cnt)
-            do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, R, true>(P, C, sbuf, wbuf, nj, ax, ay, az, ps, pw, c0, t0 + lane);
-          else
-            do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, R, false>(P, C, sbuf, wbuf, nj, ax, ay, az, ps, pw, 0, 0);
+          const bool sf = self && c0 < t0 + cnt;
+#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0 + lane)
+          for (int j = 0;;) {
+            if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
+            else if (RMAX == 4) {
+              switch (nr) {                               // partially filled tiles evaluate only the primaries they hold
+                case 1: j = FCFC_CHUNK(1, false); break;
+                case 2: j = FCFC_CHUNK(2, false); break;
+                case 3: j = FCFC_CHUNK(3, false); break;
+                default: j = FCFC_CHUNK(4, false); break;
+              }
+            } else j = (nr == 1) ? FCFC_CHUNK(1, false) : FCFC_CHUNK(RMAX, false);
+            if (j >= nj) break;
+            // a queue may overflow: the one place where queued pairs are binned
+            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, RMAX, P.qdepth / 4);
+          }
+#undef FCFC_CHUNK
         }
         b = piece_end;
       }
@@ -412,6 +612,8 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
       sweep_range(b, e, sax, say, saz, sbx, sby, sbz, q < 0);
     }
   }
+  // whatever is still queued
+  drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, P.qdepth, 0);
 
   // ---- block epilogue: flush the histogram ----
   __syncthreads();

@@ -15,6 +15,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -501,14 +502,51 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   int dev = 0; cudaGetDevice(&dev);
   int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int nmutab = (bintype == BIN_SMU) ? nmu * nmu : 0;
-  SmemPlan pl = withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true)
-                       : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true);
-  v.smem_hist = pl.total + 1024 <= smem_max;
-  if (!v.smem_hist) {
-    pl = withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), false)
-                : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), false);
-    if (pl.total + 1024 > smem_max) { cudaFree(dbuf); set_err("lookup tables do not fit in shared memory (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  // accepted-pair queues: the deepest power-of-two depth that fits next to the histogram and tables
+  const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
+  auto plan = [&](bool sh, int depth, bool tg) {
+    return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg)
+                  : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
+  };
+  int qdepth_max = 64;
+  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd));
+  // preference order: everything in shared memory with deep queues > tables in global memory >
+  // shallow queues > histogram in global memory (large tables / histograms are rare)
+  SmemPlan pl; int depth = 0; bool tabs_global = false; v.smem_hist = true;
+  const struct { bool sh, tg; int dmin; } tries[] = {{true, false, 16}, {true, true, 16}, {true, false, 8}, {true, true, 8},
+                                                     {false, false, 16}, {false, true, 8}};
+  for (auto &t : tries) {
+    for (int d = qdepth_max; d >= t.dmin && !depth; d >>= 1) {
+      pl = plan(t.sh, d, t.tg);
+      if (pl.total + 1024 <= smem_max) { depth = d; v.smem_hist = t.sh; tabs_global = t.tg; }
+    }
+    if (depth) break;
   }
+  if (!depth) { cudaFree(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  P.tabs_global = tabs_global;
+  if (tabs_global) v.generic = true;            // only the generic variant reads tables through global pointers
+  if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
+  // tables that are pure functions of the index are computed in registers instead of looked up
+  {
+    auto is_sqrt = [](const void *tab, int width, long n) {
+      if (!tab || n <= 0 || n > (1 << 18)) return 0;
+      for (long i = 0; i < n; i++) {
+        long v = width ? ((const uint16_t *) tab)[i] : ((const uint8_t *) tab)[i];
+        long r = (long) std::floor(std::sqrt((double) i)); while (r * r > i) r--; while ((r + 1) * (r + 1) <= i) r++;
+        if (v != r) return 0;
+      }
+      return 1;
+    };
+    P.mu_is_sqrt = (bintype == BIN_SMU) ? is_sqrt(b->mutab, 0, (long) nmu * nmu) : 0;
+    P.stab_is_sqrt = (b->tabtype == FCFC_GPU_TAB_INT && s2bin[0] == 0) ? is_sqrt(b->stab, b->swidth, nstab) : 0;
+    P.ptab_is_ident = 0;
+    if (bintype == BIN_SPI && b->periodic && b->tabtype == FCFC_GPU_TAB_INT && pbin[0] == 0 && nptab == np) {
+      P.ptab_is_ident = 1;
+      for (long i = 0; i < nptab; i++) { long vv = b->pwidth ? ((const uint16_t *) b->ptab)[i] : ((const uint8_t *) b->ptab)[i]; if (vv != i) P.ptab_is_ident = 0; }
+    }
+    if (getenv("FCFC_GPU_NO_TABLE_MATH")) P.mu_is_sqrt = P.stab_is_sqrt = P.ptab_is_ident = 0;
+  }
+  P.qdepth = depth;
   cudaEventRecord(ev1);
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + kWarpsPerBlock - 1) / kWarpsPerBlock));
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);

@@ -177,7 +177,8 @@ def test_huge_histogram_uses_global_path(gpu):
 
 def test_with_mu_one(gpu):
     kw = dict(box=200.0, bintype=1, smax=40.0, ds=2.0, nmu=20, with_mu_one=True)
-    x, y, z, _ = lattice_box_catalog(3000, 200.0, 52)     # lattice: many pairs exactly along z (mu = 1)
+    x, y, z, _ = lattice_box_catalog(3000, 200.0, 52)
+    x[1000:2000], y[1000:2000] = x[:1000], y[:1000]     # 1000 pairs exactly along z (mu = 1)
     for prec in ("double", "float"):
         got = gpu_counts(gpu, kw, True, prec, [(x, y, z)], ["DD"], False)["DD"]
         ob = oracle.setup(prec=prec[0], periodic=True, **kw)
