@@ -1,0 +1,147 @@
+/*******************************************************************************
+* fcfc_b200/host/fcfc_gpu_shim.c -- C99 host shim: FCFC's counting seam on top of libfcfc_b200.so.
+*
+* Drop-in for three translation units of cheng-zhao/FCFC v1.0.1:
+*     src/tree/kdtree.c, src/tree/balltree.c   (the spatial index; qselect.c / pca.c become unused)
+*     src/fcfc/2pt_box/count_func.c  or  src/fcfc/2pt/count_func.c   (the counting core)
+* Everything else of the host -- load_conf, cf_setup, the catalogue readers, cnvt_coord,
+* tree_create / tree_destroy (build_tree.c), eval_cf, save_res -- is compiled UNMODIFIED.  The
+* reference's tree_create() keeps reading, rescaling and weighting the catalogue on the host
+* (build_tree.c:84-156) and then calls create_kdtree()/create_balltree(): here that call uploads
+* the arrays to the GPU and returns the catalogue handle in place of the tree root.  count_pairs()
+* (called from eval_cf.c:119,142) marshals the slice of `CF` the counter reads into fcfc_gpu_bins.
+*
+* Compile once per program with the reference's include paths (see integration/Makefile):
+*     -Isrc/fcfc/2pt_box (or 2pt)  -Isrc/util -Isrc/io -Isrc/lib -Isrc/math -Isrc/tree  -Iinclude
+* The same -DSINGLE_PREC / -DWITH_MU_ONE switches as the rest of the host apply.  -DOMP/-DWITH_SIMD
+* may stay enabled for the readers; -DMPI is not supported (one process drives all GPUs).
+*
+* Environment: FCFC_GPU_ARITH=fma selects the FMA evaluation order of the reference's AVX-512 kernels
+* (default: the scalar order, bit-exact against the reference's scalar code path);
+* FCFC_GPU_DEVICES=0,1,... restricts the devices; FCFC_GPU_VERBOSE=1 prints engine diagnostics.
+*******************************************************************************/
+#include "define.h"
+#include "eval_cf.h"
+#include "count_func.h"
+#include "kdtree.h"
+#include "balltree.h"
+#include "fcfc_gpu.h"
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#ifdef MPI
+  #error the GPU engine replaces MPI: build the host without -DMPI
+#endif
+
+#ifdef SINGLE_PREC
+  #define SHIM_IS_FLOAT 1
+#else
+  #define SHIM_IS_FLOAT 0
+#endif
+#ifdef FCFC_METRIC_PERIODIC
+  #define SHIM_PERIODIC 1
+#else
+  #define SHIM_PERIODIC 0
+#endif
+
+static int shim_ready = 0;
+
+static void shim_init(void) {
+  if (shim_ready) return;
+  int dev[64], ndev = 0;
+  const char *s = getenv("FCFC_GPU_DEVICES");
+  if (s) {
+    char *copy = strdup(s), *save = NULL;
+    for (char *t = strtok_r(copy, ",", &save); t && ndev < 64; t = strtok_r(NULL, ",", &save)) dev[ndev++] = atoi(t);
+    free(copy);
+  }
+  const char *v = getenv("FCFC_GPU_VERBOSE");
+  int n = fcfc_gpu_init(ndev, ndev ? dev : NULL, v ? atoi(v) : 0);
+  if (n <= 0) {
+    P_ERR("GPU engine initialisation failed: %s\n", fcfc_gpu_last_error());
+    exit(FCFC_ERR_TREE);
+  }
+  shim_ready = 1;
+}
+
+/* Upload one catalogue; the handle stands in for the tree root (it is only ever passed back to
+ * count_pairs() and *_free()).  The coordinates are already rescaled, the survey build's 4th
+ * column already holds x^2+y^2+z^2 (2pt/build_tree.c:35-133). */
+static void *shim_upload(real *x[static FCFC_XDIM], real *w, const size_t ndata, size_t *nnode) {
+  shim_init();
+  const void *s = NULL;
+#if FCFC_XDIM > 3
+  s = x[3];
+#endif
+  fcfc_gpu_catalog *cat = fcfc_gpu_catalog_create(x[0], x[1], x[2], s, w, ndata, SHIM_IS_FLOAT, 1.0, -1);
+  if (!cat) {
+    P_ERR("failed to build the GPU cell list: %s\n", fcfc_gpu_last_error());
+    return NULL;
+  }
+  if (nnode) *nnode = 1;
+  return cat;
+}
+
+KDT *create_kdtree(real *x[static FCFC_XDIM], real *w, const size_t ndata,
+#ifdef FCFC_METRIC_PERIODIC
+    const real bsize[static 3],
+#endif
+    const size_t nleaf, size_t *nnode) {
+#ifdef FCFC_METRIC_PERIODIC
+  (void) bsize;
+#endif
+  (void) nleaf;
+  return (KDT *) shim_upload(x, w, ndata, nnode);
+}
+
+void kdtree_free(KDT *root) { fcfc_gpu_catalog_destroy((fcfc_gpu_catalog *) root); }
+
+BLT *create_balltree(real *x[static FCFC_XDIM], real *w, const size_t ndata,
+#ifdef FCFC_METRIC_PERIODIC
+    const real bsize[static 3],
+#endif
+    const size_t nleaf, size_t *nnode) {
+#ifdef FCFC_METRIC_PERIODIC
+  (void) bsize;
+#endif
+  (void) nleaf;
+  return (BLT *) shim_upload(x, w, ndata, nnode);
+}
+
+void balltree_free(BLT *root) { fcfc_gpu_catalog_destroy((fcfc_gpu_catalog *) root); }
+
+/* count_pairs(): same signature and semantics as count_func.h:54 (auto pairs once, raw counts into
+ * cnt[].i or weighted sums into cnt[].d, layout s + p * ns).  eval_cf.c ignores the return value, so
+ * errors terminate the program like the reference's own fatal paths (count_func.c:77-95). */
+int count_pairs(const void *tree1, const void *tree2, CF *cf, COUNT *cnt,
+    const bool isauto, const bool withwt) {
+  fcfc_gpu_bins b;
+  memset(&b, 0, sizeof b);
+  b.bintype = cf->bintype;
+  b.periodic = SHIM_PERIODIC;
+  b.is_float = SHIM_IS_FLOAT;
+  b.tabtype = cf->tabtype;
+  b.ns = cf->ns; b.np = cf->np; b.nmu = cf->nmu;
+  b.swidth = cf->swidth; b.pwidth = cf->pwidth;
+#ifdef WITH_MU_ONE
+  b.with_mu_one = 1;
+#endif
+  const char *ar = getenv("FCFC_GPU_ARITH");
+  b.arith = (ar && !strcmp(ar, "fma")) ? FCFC_GPU_ARITH_FMA : FCFC_GPU_ARITH_SCALAR;
+  b.s2bin = cf->s2bin;
+#ifdef FCFC_METRIC_PERIODIC
+  b.pbin = cf->pbin;
+  for (int i = 0; i < 3; i++) b.bsize[i] = cf->bsize[i];
+#else
+  b.pbin = cf->p2bin;
+#endif
+  b.stab = cf->stab; b.ptab = cf->ptab; b.mutab = cf->mutab;
+  int e = fcfc_gpu_count((fcfc_gpu_catalog *) tree1, (fcfc_gpu_catalog *) tree2, &b, isauto, withwt,
+      withwt ? NULL : (int64_t *) cnt, withwt ? (double *) cnt : NULL);
+  if (e) {
+    P_ERR("GPU pair counting failed (%d): %s\n", e, fcfc_gpu_last_error());
+    exit(FCFC_ERR_CF);
+  }
+  return 0;
+}
