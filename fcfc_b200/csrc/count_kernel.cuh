@@ -375,39 +375,133 @@ __device__ __forceinline__ int bin_entry(const CountParams<T> &P, const BlockCtx
   }
 }
 
-// Pop and bin entries.  Called when the fullest queue may overflow: if it really is close to full,
-// `rounds` entries are popped from every lane (two per iteration for instruction-level parallelism);
-// lanes that run dry simply idle.  Returns the new upper bound of the fullest queue (entries).
-template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int NW>
-__device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockCtx<T> &C, LaneQueue<T, NW> &Q, int need, int keep) {
+// ---------------------------------------------------------------------------------------------
+// Shared-window (32-bit address) helpers for the drain: no generic-address arithmetic in the hot loop.
+__device__ __forceinline__ void red_shared_u32(unsigned a, bool p) {
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.u32 [%1], 1;}" ::"r"((int) p), "r"(a) : "memory");
+}
+__device__ __forceinline__ void red_shared_f64(unsigned a, double v, bool p) {
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.f64 [%1], %2;}" ::"r"((int) p), "r"(a), "d"(v) : "memory");
+}
+__device__ __forceinline__ int lds_u8(unsigned a, bool p) {
+  unsigned v = 0;
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %1, 0; @q ld.shared.u8 %0, [%2];}" : "+r"(v) : "r"((int) p), "r"(a) : "memory");
+  return (int) v;
+}
+struct FastCtx { unsigned hist_s, stab_s, ptab_s, mutab_s; };
+
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
+
+// floor(d2) and floor(sqrt(floor(d2))) for 0 <= d2 < 2^18; float: no int<->float conversion needed.
+__device__ __forceinline__ void floor_and_isqrt(float d2, int &fl, int &rt) {
+  const float t = __fadd_rz(d2, 8388608.0f);            // mantissa = floor(d2)
+  fl = __float_as_int(t) - 0x4B000000;
+  float r;
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t - 8388607.5f));     // sqrt(floor(d2) + 1/2), exact argument
+  rt = __float_as_int(__fadd_rz(r, 8388608.0f)) - 0x4B000000;
+}
+__device__ __forceinline__ void floor_and_isqrt(double d2, int &fl, int &rt) {
+  fl = trunc_pos(d2);
+  rt = isqrt_small(fl);
+}
+
+// Fast, exact-or-flagged mu bin: j = floor(nmu * sqrt(num / d2)) from approximate reciprocal and square
+// root.  The reference's index floor(sqrt(floor(fl(fl(num/d2) * nmu^2)))) can differ from j only when
+// nmu*mu lies within ~1.2e-4 of an integer (error budget in DESIGN.md); those pairs, pairs with
+// d2 < EPS and mu >= 1 are flagged `amb` and re-binned with the exact IEEE sequence.
+__device__ __forceinline__ int mu_bin_fast(float num, float d2, float nmu_f, int nmu, float eps, bool &amb) {
+  float r, st;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
+  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(st) : "f"(num * r));
+  st *= nmu_f;
+  const float jf = __fadd_rz(st, 8388608.0f);
+  const int j = __float_as_int(jf) - 0x4B000000;
+  const float frac = st - (jf - 8388608.0f);
+  amb = !((frac > 2.44140625e-4f) && (frac < 1.0f - 2.44140625e-4f) && (j < nmu) && (d2 >= eps));
+  return j;
+}
+
+// Drain of the fast variants (box or isotropic, shared-memory histogram, 8-bit integer tables, zero lower
+// bounds).  Two entries per lane and iteration, branch-free apart from the rare exact re-binning.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
+__device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
+                                           LaneQueue<T, NW> &Q, int rounds) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  const int mx = (int) (__reduce_max_sync(0xffffffffu, Q.fill_bytes()) / S);
-  if (mx + need <= P.qdepth - 1) return mx;
-  const int rounds = mx - keep;
+  const float nmu_f = (float) (int) sqrtf((float) P.nmu2), eps = (float) Ar<T>::eps();
+  const int nmu = (int) nmu_f;
 #pragma unroll 1
   for (int k = 0; k < rounds; k += 2) {
     const unsigned int fill = Q.fill_bytes();
     const bool h0 = fill != 0, h1 = fill > S;
     const unsigned int p0 = Q.rptr, p1 = Q.next(p0);
-    T e0[NW], e1[NW];
-    QOps<T, NW>::load(p0, e0);
-    QOps<T, NW>::load(p1, e1);
+    T e[2][NW];
+    QOps<T, NW>::load(p0, e[0]);
+    QOps<T, NW>::load(p1, e[1]);
     Q.rptr = h1 ? Q.next(p1) : (h0 ? p1 : p0);
-    T w0 = 0, w1 = 0;
-    int b0 = -1, b1 = -1;
-    if (!GENERIC && (BOX || BIN == BIN_ISO)) {
-      // branch-free: slots past the tail hold stale data, zero them so that every table index stays in range
+    int bin[2]; bool amb[2]; T w[2];
 #pragma unroll
-      for (int i = 0; i < NW; i++) { e0[i] = h0 ? e0[i] : (T) 0; e1[i] = h1 ? e1[i] : (T) 0; }
-      b0 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e0, w0);
-      b1 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e1, w1);
-    } else {
-      if (h0) b0 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e0, w0);
-      if (h1) b1 = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e1, w1);
+    for (int i = 0; i < 2; i++) {
+      const bool h = i ? h1 : h0;
+      const T d2 = e[i][0];
+      int si, sb;
+      floor_and_isqrt(d2, si, sb);
+      if (!P.stab_is_sqrt) sb = lds_u8(F.stab_s + (unsigned) si, h);
+      int pb = 0;
+      amb[i] = false;
+      if (BIN == BIN_SMU) {
+        pb = mu_bin_fast(to_f32(e[i][1 % NW]), to_f32(d2), nmu_f, nmu, eps, amb[i]);
+        if (!P.mu_is_sqrt) amb[i] = true;
+      } else if (BIN == BIN_SPI) {
+        pb = trunc_pos(e[i][1 % NW]);
+        if (!P.ptab_is_ident) pb = lds_u8(F.ptab_s + (unsigned) pb, h);
+      }
+      bin[i] = sb + pb * P.ns;
+      amb[i] = amb[i] && h;
+      w[i] = WT ? e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW] : (T) 1;
     }
-    if (h0 && b0 >= 0) hist_add<T, WT, SMEMHIST>(C, b0, w0);
-    if (h1 && b1 >= 0) hist_add<T, WT, SMEMHIST>(C, b1, w1);
+    if (BIN == BIN_SMU && __any_sync(0xffffffffu, amb[0] || amb[1])) {
+#pragma unroll
+      for (int i = 0; i < 2; i++)
+        if (amb[i]) { T ww; bin[i] = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, C, e[i], ww); }
+    }
+#pragma unroll
+    for (int i = 0; i < 2; i++) {
+      const bool ok = (i ? h1 : h0) && bin[i] >= 0;
+      if (WT) red_shared_f64(F.hist_s + 8u * (unsigned) bin[i], (double) w[i], ok);
+      else red_shared_u32(F.hist_s + 4u * (unsigned) bin[i], ok);
+    }
   }
+}
+
+// Drain of every other variant: exact per-entry binning through finish_pair.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int NW>
+__device__ __forceinline__ void drain_generic(const CountParams<T> &P, const BlockCtx<T> &C, LaneQueue<T, NW> &Q, int rounds) {
+#pragma unroll 1
+  for (int k = 0; k < rounds; k++) {
+    if (Q.fill_bytes() != 0) {
+      T e[NW];
+      QOps<T, NW>::load(Q.rptr, e);
+      Q.rptr = Q.next(Q.rptr);
+      T w;
+      const int b = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e, w);
+      if (b >= 0) hist_add<T, WT, SMEMHIST>(C, b, w);
+    }
+  }
+}
+
+// Pop and bin entries.  Called when the fullest queue may overflow: if it really is close to full, every lane
+// pops until the fullest queue is down to `keep` entries; lanes that run dry simply idle.  Returns the new
+// upper bound of the fullest queue (entries).
+template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int NW>
+__device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
+                                           LaneQueue<T, NW> &Q, int need, int keep) {
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  const int mx = (int) (__reduce_max_sync(0xffffffffu, Q.fill_bytes()) / S);
+  if (mx + need <= P.qdepth - 1) return mx;
+  const int rounds = mx - keep;
+  if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
+  else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
   return max(keep, 0);
 }
 
@@ -476,7 +570,15 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
   if (BIN == BIN_SPI) for (int i = threadIdx.x; i <= P.np; i += kThreads) s_pbin[i] = P.pbin[i];
   for (int i = threadIdx.x; i < P.nrows; i += kThreads) s_rows[i] = P.rows[i];
   if (threadIdx.x == 0) *s_blk_evals = 0;
+  // queues start zeroed: slots past a queue's tail are read (and ignored) by the two-entry drain
+  for (int i = threadIdx.x * 16; i < (kWarpsPerBlock + 1) * pl.queue_per_warp; i += kThreads * 16)
+    *reinterpret_cast<uint4 *>(smem + pl.off_queue + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
+  FastCtx F;
+  F.hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
+  F.stab_s = (unsigned int) __cvta_generic_to_shared(s_stab);
+  F.ptab_s = (unsigned int) __cvta_generic_to_shared(s_ptab);
+  F.mutab_s = (unsigned int) __cvta_generic_to_shared(s_mutab);
 
   Vec4<T> *sbuf = reinterpret_cast<Vec4<T> *>(smem + pl.off_stage + warp * pl.stage_per_warp);
   T *wbuf = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sbuf) + 32 * sizeof(Vec4<T>));
@@ -572,7 +674,7 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
             } else j = (nr == 1) ? FCFC_CHUNK(1, false) : FCFC_CHUNK(RMAX, false);
             if (j >= nj) break;
             // a queue may overflow: the one place where queued pairs are binned
-            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, RMAX, P.qdepth / 4);
+            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, RMAX, P.qdepth / 4);
           }
 #undef FCFC_CHUNK
         }
@@ -613,7 +715,7 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
     }
   }
   // whatever is still queued
-  drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, P.qdepth, 0);
+  drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, P.qdepth, 0);
 
   // ---- block epilogue: flush the histogram ----
   __syncthreads();
