@@ -34,8 +34,9 @@ namespace fcfc {
 enum { BIN_ISO = 0, BIN_SMU = 1, BIN_SPI = 2 };
 enum { ARITH_SCALAR = 0, ARITH_FMA = 1 };
 
-constexpr int kWarpsPerBlock = 16;
-constexpr int kThreads = kWarpsPerBlock * 32;
+// Warps per block (one block per SM): as many as the register file allows -- the kernels are latency bound
+// at 4 warps per scheduler.  float variants use <= 102 registers (20 warps), double variants <= 128 (16 warps).
+template <class T> struct BlockShape { static constexpr int kWarps = (sizeof(T) == 4) ? 20 : 16; static constexpr int kThreads = kWarps * 32; };
 constexpr int kMaxRows = 1024;          // stencil rows kept in shared memory
 constexpr int kSegPieceMax = 1 << 19;   // secondary points per overflow-accounting piece
 
@@ -117,6 +118,7 @@ template <int BIN, bool BOX, bool WT> struct QFmt {
 template <class T, bool WT>
 __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, int nptab_bytes, int nmutab_bytes,
                                                    int ns, int np, int nrows, bool smem_hist, int qwords, int qdepth, bool tabs_global) {
+  constexpr int kWarpsPerBlock = BlockShape<T>::kWarps;
   SmemPlan p;
   int o = 0;
   auto al = [](int v) { return (v + 15) & ~15; };
@@ -133,7 +135,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, in
   o += kWarpsPerBlock * p.stage_per_warp;
   p.off_queue = o;
   p.queue_per_warp = qdepth * 32 * qwords * (int) sizeof(T);
-  o += (kWarpsPerBlock + 1) * p.queue_per_warp;       // + one queue of slack: the region is aligned at run time
+  o += kWarpsPerBlock * p.queue_per_warp;
   p.total = o;
   return p;
 }
@@ -160,14 +162,14 @@ __device__ __forceinline__ int lut(const uint8_t *tab, int width, int hybrid, in
 
 // Second half of a pair: everything after the cheap range test.  Returns the histogram bin or -1.
 //   d2  : squared separation (ISO, SMU; survey SPI: s^2 = s - t before the pi^2 subtraction)
-//   aux : box SMU dz^2 | box SPI pi | survey SMU/SPI t (twice the dot product)
+//   aux : box SMU dz (squared again here: same rounding as in eval_pair) | box SPI pi | survey SMU/SPI t
 template <class T, int BIN, bool BOX, int ARITH, bool GENERIC>
 __device__ __forceinline__ int finish_pair(const CountParams<T> &P, const BlockCtx<T> &C, T d2, T aux, T as, T bs) {
   using A = Ar<T>;
   int pb = 0;
   T pival = aux;
   if (BIN == BIN_SMU || (BIN == BIN_SPI && !BOX)) {
-    T num = aux;
+    T num = BOX ? A::mul(aux, aux) : aux;
     if (!BOX) {               // survey: pi^2 = (s1 - s2)^2 / (s + t), 2pt/metric_common.c:180-181
       T s = A::add(as, bs);
       T d = A::sub(as, bs);
@@ -224,7 +226,7 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
       if (ARITH == ARITH_SCALAR) d2 = A::add(A::add(A::mul(dx, dx), A::mul(dy, dy)), dz2);     // :170-172
       else if (BOX) d2 = A::fma(dy, dy, A::fma(dx, dx, dz2));                                   // :426-430
       else d2 = A::fma(dz, dz, A::fma(dy, dy, A::mul(dx, dx)));                                 // 2pt/:330-333
-      aux = dz2;
+      aux = (BOX && BIN == BIN_SMU) ? dz : dz2;
       ok = d2 < P.s2max;
     }
   } else {                                      // survey (s,mu) / (s_perp,pi): 2pt/metric_common.c:169-172, 341-357
@@ -262,16 +264,17 @@ __device__ __forceinline__ void sweep_hist(unsigned int *h, unsigned long long *
 }
 
 // ---------------------------------------------------------------------------------------------
-// Per-lane circular queues of accepted pairs, addressed with 32-bit shared-window addresses.
-// Layout: [slot][lane][NW words]; a warp-wide push or pop touches 32 consecutive entries (no bank
-// conflicts).  The queue of a warp is aligned to its own size so that advancing a pointer is
-// ptr = (ptr & ~amask) | ((ptr + stride) & amask): one add and one LOP3.
+// Per-lane stacks of accepted pairs, addressed with 32-bit shared-window addresses.
+// Layout: [slot][lane][NW words]; a warp-wide push or pop touches 32 consecutive entries (no bank conflicts).
 template <class T, int NW> struct QOps;
+// push: predicated store + predicated pointer bump in one asm block (a stack: no wrap-around arithmetic)
+#define FCFC_PUSH_ASM(ST) "{.reg .pred q; setp.ne.s32 q, %1, 0; " ST " @q add.u32 %0, %0, %2;}"
 template <int NW> struct QOps<float, NW> {
-  static __device__ __forceinline__ void store(unsigned a, const float (&v)[NW], bool p) {
-    if (NW == 1) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f32 [%1], %2;}" ::"r"((int) p), "r"(a), "f"(v[0]) : "memory");
-    else if (NW == 2) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f32 [%1], {%2, %3};}" ::"r"((int) p), "r"(a), "f"(v[0]), "f"(v[1 % NW]) : "memory");
-    else asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v4.f32 [%1], {%2, %3, %4, %5};}" ::"r"((int) p), "r"(a), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]) : "memory");
+  static __device__ __forceinline__ void push(unsigned &w, const float (&v)[NW], bool p) {
+    constexpr unsigned S = 32u * NW * sizeof(float);
+    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f32 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]) : "memory");
+    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f32 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]) : "memory");
+    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v4.f32 [%0], {%3, %4, %5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]) : "memory");
   }
   static __device__ __forceinline__ void load(unsigned a, float (&v)[NW]) {
     if (NW == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a) : "memory");
@@ -280,12 +283,11 @@ template <int NW> struct QOps<float, NW> {
   }
 };
 template <int NW> struct QOps<double, NW> {
-  static __device__ __forceinline__ void store(unsigned a, const double (&v)[NW], bool p) {
-    if (NW == 1) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.f64 [%1], %2;}" ::"r"((int) p), "r"(a), "d"(v[0]) : "memory");
-    else {
-      asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f64 [%1], {%2, %3};}" ::"r"((int) p), "r"(a), "d"(v[0]), "d"(v[1 % NW]) : "memory");
-      if (NW == 4) asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q st.shared.v2.f64 [%1+16], {%2, %3};}" ::"r"((int) p), "r"(a), "d"(v[2 % NW]), "d"(v[3 % NW]) : "memory");
-    }
+  static __device__ __forceinline__ void push(unsigned &w, const double (&v)[NW], bool p) {
+    constexpr unsigned S = 32u * NW * sizeof(double);
+    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f64 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]) : "memory");
+    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]) : "memory");
+    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4}; @q st.shared.v2.f64 [%0+16], {%5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]), "d"(v[2 % NW]), "d"(v[3 % NW]) : "memory");
   }
   static __device__ __forceinline__ void load(unsigned a, double (&v)[NW]) {
     if (NW == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a) : "memory");
@@ -295,18 +297,15 @@ template <int NW> struct QOps<double, NW> {
     }
   }
 };
+#undef FCFC_PUSH_ASM
 
+// Per-lane LIFO of accepted pairs (the order in which pairs reach the histogram is irrelevant).
 template <class T, int NW> struct LaneQueue {
-  unsigned int wptr, rptr;      // shared addresses of the next free slot / the oldest entry (this lane's column)
-  unsigned int amask;           // queue bytes per warp - 1
+  unsigned int top;             // shared address of this lane's next free slot
+  unsigned int base;            // shared address of this lane's slot 0
   static constexpr unsigned int kStride = 32u * NW * sizeof(T);
-  __device__ __forceinline__ unsigned int next(unsigned int p) const { return (p & ~amask) | ((p + kStride) & amask); }
-  __device__ __forceinline__ void push(const T (&v)[NW], bool ok) {
-    QOps<T, NW>::store(wptr, v, ok);
-    const unsigned int n = next(wptr);
-    wptr = ok ? n : wptr;
-  }
-  __device__ __forceinline__ unsigned int fill_bytes() const { return (wptr - rptr) & amask; }
+  __device__ __forceinline__ void push(const T (&v)[NW], bool ok) { QOps<T, NW>::push(top, v, ok); }
+  __device__ __forceinline__ unsigned int fill_bytes() const { return top - base; }
 };
 
 // Truncation of 0 <= x < 2^23 (float) / 2^31 (double) without the quarter-rate F2I: add 2^23 (2^52)
@@ -346,7 +345,7 @@ __device__ __forceinline__ int bin_entry(const CountParams<T> &P, const BlockCtx
     int pb = 0;
     bool ok = true;
     if (BIN == BIN_SMU) {
-      const T dz2 = e[1 % NW];
+      const T dz2 = A::mul(e[1 % NW], e[1 % NW]);    // the queue holds dz
       int m;
       if (ARITH == ARITH_SCALAR) {              // metric_common.c:184
         m = trunc_pos(A::mul(A::div(dz2, d2), P.nmu2f));
@@ -393,74 +392,71 @@ struct FastCtx { unsigned hist_s, stab_s, ptab_s, mutab_s; };
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
 
-// floor(d2) and floor(sqrt(floor(d2))) for 0 <= d2 < 2^18; float: no int<->float conversion needed.
-__device__ __forceinline__ void floor_and_isqrt(float d2, int &fl, int &rt) {
-  const float t = __fadd_rz(d2, 8388608.0f);            // mantissa = floor(d2)
-  fl = __float_as_int(t) - 0x4B000000;
+// Fast bins of a box / isotropic pair from ONE approximate reciprocal square root r = rsqrt(d2):
+//   s        = d2 * r            -> s bin  floor(s)   (floor(sqrt(floor(d2))) == floor(sqrt(d2)) exactly)
+//   nmu * mu = nmu * |dz| * r    -> mu bin floor(.)   (== floor(sqrt(floor(fl(fl(dz2/d2)*nmu^2)))) away from bin edges)
+// Both are computed scaled by 4096 and truncated by adding 2^23 toward zero: the mantissa then holds
+// floor(4096 x) = bin * 4096 + 12 fraction bits.  The approximations (rsqrt.approx 2^-22 rel., three multiplies)
+// move s by < 40 * 5e-7 and nmu*mu by < 255 * 5e-7, the reference's own roundings move nmu*mu by < 255 * 1.8e-7,
+// all far below 2^-12: a pair whose fraction bits are 0x000 or 0xFFF (within 2^-12 of a bin edge), d2 < EPS or
+// mu >= 1 is flagged and re-binned by the caller with the exact IEEE sequence (bin_entry).
+constexpr int kMantBias = 0x4B000000 >> 12;     // exponent bits of 2^23, shifted like the mantissa
+// Integer work is kept off the (half-rate) ALU pipe where possible: the +1 rides on an FFMA, the shifts are
+// IMAD.HI, the edge test is one AND per quantity, one IMAD and one compare.  A pair is flagged when the 12
+// fraction bits of 4096*x are in {0xFFF, 0, 1, 2} (x within [-2^-12, 3*2^-12) of an integer): this also
+// catches d2 < EPS (s < 3/4096) and mu >= 1 (nmu*mu within the band of nmu; it cannot exceed it by more).
+template <int BIN>
+__device__ __forceinline__ int fast_bins(float d2, float dz, float nmu_f, int ns, bool &amb) {
   float r;
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(t - 8388607.5f));     // sqrt(floor(d2) + 1/2), exact argument
-  rt = __float_as_int(__fadd_rz(r, 8388608.0f)) - 0x4B000000;
-}
-__device__ __forceinline__ void floor_and_isqrt(double d2, int &fl, int &rt) {
-  fl = trunc_pos(d2);
-  rt = isqrt_small(fl);
-}
-
-// Fast, exact-or-flagged mu bin: j = floor(nmu * sqrt(num / d2)) from approximate reciprocal and square
-// root.  The reference's index floor(sqrt(floor(fl(fl(num/d2) * nmu^2)))) can differ from j only when
-// nmu*mu lies within ~1.2e-4 of an integer (error budget in DESIGN.md); those pairs, pairs with
-// d2 < EPS and mu >= 1 are flagged `amb` and re-binned with the exact IEEE sequence.
-__device__ __forceinline__ int mu_bin_fast(float num, float d2, float nmu_f, int nmu, float eps, bool &amb) {
-  float r, st;
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2));
-  asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(st) : "f"(num * r));
-  st *= nmu_f;
-  const float jf = __fadd_rz(st, 8388608.0f);
-  const int j = __float_as_int(jf) - 0x4B000000;
-  const float frac = st - (jf - 8388608.0f);
-  amb = !((frac > 2.44140625e-4f) && (frac < 1.0f - 2.44140625e-4f) && (j < nmu) && (d2 >= eps));
-  return j;
+  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2 + 1e-30f));      // d2 = 0 (coincident points): finite r, s = 0 -> flagged
+  r *= 4096.0f;
+  const unsigned int us = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(d2, r, 1.0f), 8388608.0f));   // bias + floor(4096 s) + 1
+  unsigned int t = us & 0xFFCu;
+  int bin = (int) __umulhi(us, 1u << 20);       // us >> 12 = kMantBias + s bin
+  if (BIN == BIN_SMU) {
+    const unsigned int um = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(fabsf(dz) * r, nmu_f, 1.0f), 8388608.0f));
+    t *= (um & 0xFFCu);
+    bin += (int) __umulhi(um, 1u << 20) * ns;   // + (kMantBias + mu bin) * ns
+  }
+  amb = (t == 0u);
+  return bin - kMantBias * ((BIN == BIN_SMU) ? ns + 1 : 1);
 }
 
 // Drain of the fast variants (box or isotropic, shared-memory histogram, 8-bit integer tables, zero lower
-// bounds).  Two entries per lane and iteration, branch-free apart from the rare exact re-binning.
+// bounds): every lane pops `rounds` entries off its stack (lanes with fewer idle), two per iteration,
+// branch-free apart from the rare exact re-binning.
 template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
 __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
                                            LaneQueue<T, NW> &Q, int rounds) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  const float nmu_f = (float) (int) sqrtf((float) P.nmu2), eps = (float) Ar<T>::eps();
-  const int nmu = (int) nmu_f;
+  const float nmu_f = (float) (int) sqrtf((float) P.nmu2);
+  const int mine = min((int) (Q.fill_bytes() / S), rounds);     // entries this lane pops
+  Q.top -= (unsigned int) mine * S;
+  unsigned int rp = Q.top;
+  const bool table_math = P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt);
 #pragma unroll 1
-  for (int k = 0; k < rounds; k += 2) {
-    const unsigned int fill = Q.fill_bytes();
-    const bool h0 = fill != 0, h1 = fill > S;
-    const unsigned int p0 = Q.rptr, p1 = Q.next(p0);
+  for (int k = 0; k < rounds; k += 2, rp += 2 * S) {
+    const bool h0 = k < mine, h1 = k + 1 < mine;
     T e[2][NW];
-    QOps<T, NW>::load(p0, e[0]);
-    QOps<T, NW>::load(p1, e[1]);
-    Q.rptr = h1 ? Q.next(p1) : (h0 ? p1 : p0);
+    QOps<T, NW>::load(rp, e[0]);
+    QOps<T, NW>::load(rp + S, e[1]);            // slots above the old top hold stale (zeroed or older) entries: ignored
     int bin[2]; bool amb[2]; T w[2];
 #pragma unroll
     for (int i = 0; i < 2; i++) {
       const bool h = i ? h1 : h0;
-      const T d2 = e[i][0];
-      int si, sb;
-      floor_and_isqrt(d2, si, sb);
-      if (!P.stab_is_sqrt) sb = lds_u8(F.stab_s + (unsigned) si, h);
-      int pb = 0;
-      amb[i] = false;
-      if (BIN == BIN_SMU) {
-        pb = mu_bin_fast(to_f32(e[i][1 % NW]), to_f32(d2), nmu_f, nmu, eps, amb[i]);
-        if (!P.mu_is_sqrt) amb[i] = true;
-      } else if (BIN == BIN_SPI) {
-        pb = trunc_pos(e[i][1 % NW]);
+      if (BIN != BIN_SPI) {
+        bin[i] = fast_bins<BIN>(to_f32(e[i][0]), (BIN == BIN_SMU) ? to_f32(e[i][1 % NW]) : 0.0f, nmu_f, P.ns, amb[i]);
+        amb[i] = (amb[i] || !table_math) && h;
+      } else {          // box (s_perp, pi): two integer-table lookups (or identity / sqrt when the tables are that)
+        int sb, pb = trunc_pos(e[i][1 % NW]);
+        const int fl = trunc_pos(e[i][0]);
+        if (P.stab_is_sqrt) sb = isqrt_small(fl); else sb = lds_u8(F.stab_s + (unsigned) fl, h);
         if (!P.ptab_is_ident) pb = lds_u8(F.ptab_s + (unsigned) pb, h);
+        bin[i] = sb + pb * P.ns; amb[i] = false;
       }
-      bin[i] = sb + pb * P.ns;
-      amb[i] = amb[i] && h;
       w[i] = WT ? e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW] : (T) 1;
     }
-    if (BIN == BIN_SMU && __any_sync(0xffffffffu, amb[0] || amb[1])) {
+    if (BIN != BIN_SPI && __any_sync(0xffffffffu, amb[0] || amb[1])) {
 #pragma unroll
       for (int i = 0; i < 2; i++)
         if (amb[i]) { T ww; bin[i] = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, C, e[i], ww); }
@@ -477,12 +473,13 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
 // Drain of every other variant: exact per-entry binning through finish_pair.
 template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int NW>
 __device__ __forceinline__ void drain_generic(const CountParams<T> &P, const BlockCtx<T> &C, LaneQueue<T, NW> &Q, int rounds) {
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
 #pragma unroll 1
   for (int k = 0; k < rounds; k++) {
-    if (Q.fill_bytes() != 0) {
+    if (Q.top != Q.base) {
       T e[NW];
-      QOps<T, NW>::load(Q.rptr, e);
-      Q.rptr = Q.next(Q.rptr);
+      Q.top -= S;
+      QOps<T, NW>::load(Q.top, e);
       T w;
       const int b = bin_entry<T, BIN, BOX, WT, ARITH, GENERIC, NW>(P, C, e, w);
       if (b >= 0) hist_add<T, WT, SMEMHIST>(C, b, w);
@@ -538,8 +535,9 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
 }
 
 template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int RMAX>
-__global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T> P) {
+__global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const CountParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem[];
+  constexpr int kThreads = BlockShape<T>::kThreads, kWarpsPerBlock = BlockShape<T>::kWarps;
   constexpr int NW = QFmt<BIN, BOX, WT>::NW;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
@@ -571,7 +569,7 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
   for (int i = threadIdx.x; i < P.nrows; i += kThreads) s_rows[i] = P.rows[i];
   if (threadIdx.x == 0) *s_blk_evals = 0;
   // queues start zeroed: slots past a queue's tail are read (and ignored) by the two-entry drain
-  for (int i = threadIdx.x * 16; i < (kWarpsPerBlock + 1) * pl.queue_per_warp; i += kThreads * 16)
+  for (int i = threadIdx.x * 16; i < kWarpsPerBlock * pl.queue_per_warp; i += kThreads * 16)
     *reinterpret_cast<uint4 *>(smem + pl.off_queue + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   FastCtx F;
@@ -583,13 +581,8 @@ __global__ void __launch_bounds__(kThreads, 1) count_kernel(const CountParams<T>
   Vec4<T> *sbuf = reinterpret_cast<Vec4<T> *>(smem + pl.off_stage + warp * pl.stage_per_warp);
   T *wbuf = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sbuf) + 32 * sizeof(Vec4<T>));
   LaneQueue<T, NW> Q;
-  {
-    const unsigned int qbytes = (unsigned int) pl.queue_per_warp;
-    unsigned int qbase = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue);
-    qbase = (qbase + qbytes - 1) & ~(qbytes - 1);               // align to the queue size (slack reserved in the plan)
-    Q.amask = qbytes - 1;
-    Q.wptr = Q.rptr = qbase + warp * qbytes + lane * (unsigned int) (NW * sizeof(T));
-  }
+  Q.base = Q.top = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue) + warp * (unsigned int) pl.queue_per_warp
+                   + lane * (unsigned int) (NW * sizeof(T));
   int ub = 0;                   // warp-uniform upper bound of the fullest lane queue (entries)
   unsigned long long my_evals = 0;
   const int ncy = P.nc[1], ncz = P.nc[2];

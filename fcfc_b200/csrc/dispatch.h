@@ -46,7 +46,7 @@ static cudaError_t launch_count(const Variant &v, const CountParams<T> &P, int n
     auto kern = count_kernel<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, kR>;                             \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
     if (e != cudaSuccess) return e;                                                                      \
-    kern<<<nblocks, kThreads, smem_bytes>>>(P);                                                          \
+    kern<<<nblocks, BlockShape<T>::kThreads, smem_bytes>>>(P);                                                          \
     return cudaGetLastError();                                                                           \
   }
 

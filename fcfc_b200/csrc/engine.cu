@@ -548,7 +548,7 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   }
   P.qdepth = depth;
   cudaEventRecord(ev1);
-  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + kWarpsPerBlock - 1) / kWarpsPerBlock));
+  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(ev2);
