@@ -35,8 +35,14 @@ enum { BIN_ISO = 0, BIN_SMU = 1, BIN_SPI = 2 };
 enum { ARITH_SCALAR = 0, ARITH_FMA = 1 };
 
 // Warps per block (one block per SM): as many as the register file allows -- the kernels are latency bound
-// at 4 warps per scheduler.  float variants use <= 102 registers (20 warps), double variants <= 128 (16 warps).
-template <class T> struct BlockShape { static constexpr int kWarps = (sizeof(T) == 4) ? 20 : 16; static constexpr int kThreads = kWarps * 32; };
+// at 4 warps per scheduler.  float variants fit in 80 registers (24 warps), double variants <= 128 (16 warps).
+#ifndef FCFC_ABLATE
+#define FCFC_ABLATE 0
+#endif
+#ifndef FCFC_WARPS_F32
+#define FCFC_WARPS_F32 24
+#endif
+template <class T> struct BlockShape { static constexpr int kWarps = (sizeof(T) == 4) ? FCFC_WARPS_F32 : 16; static constexpr int kThreads = kWarps * 32; };
 constexpr int kMaxRows = 1024;          // stencil rows kept in shared memory
 constexpr int kSegPieceMax = 1 << 19;   // secondary points per overflow-accounting piece
 
@@ -94,6 +100,8 @@ template <class T> struct CountParams {
   int ns, np, nmu2, ntot, soff, poff;
   int tab_hybrid, swidth, pwidth, with_mu_one, smin0, pmin0;
   int mu_is_sqrt, stab_is_sqrt, ptab_is_ident;     // tables that equal floor(sqrt(i)) / i are computed, not looked up
+  // fast-bin fixed-point scales: s and nmu*mu are truncated after multiplication by 2^ks / 2^km (see fast_bins)
+  float fb_sscale, fb_mscale; unsigned int fb_smask, fb_mmask, fb_sshift, fb_mshift;
   const uint8_t *stab; const uint8_t *ptab; const uint8_t *mutab;
   int nstab, nptab;                     // entries
   const T *s2bin; const T *pbin;
@@ -272,28 +280,28 @@ template <class T, int NW> struct QOps;
 template <int NW> struct QOps<float, NW> {
   static __device__ __forceinline__ void push(unsigned &w, const float (&v)[NW], bool p) {
     constexpr unsigned S = 32u * NW * sizeof(float);
-    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f32 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]) : "memory");
-    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f32 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]) : "memory");
-    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v4.f32 [%0], {%3, %4, %5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]) : "memory");
+    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f32 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]));
+    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f32 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]));
+    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v4.f32 [%0], {%3, %4, %5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]));
   }
   static __device__ __forceinline__ void load(unsigned a, float (&v)[NW]) {
-    if (NW == 1) asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a) : "memory");
-    else if (NW == 2) asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1 % NW]) : "r"(a) : "memory");
-    else asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1 % NW]), "=f"(v[2 % NW]), "=f"(v[3 % NW]) : "r"(a) : "memory");
+    if (NW == 1) asm("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a));
+    else if (NW == 2) asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1 % NW]) : "r"(a));
+    else asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1 % NW]), "=f"(v[2 % NW]), "=f"(v[3 % NW]) : "r"(a));
   }
 };
 template <int NW> struct QOps<double, NW> {
   static __device__ __forceinline__ void push(unsigned &w, const double (&v)[NW], bool p) {
     constexpr unsigned S = 32u * NW * sizeof(double);
-    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f64 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]) : "memory");
-    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]) : "memory");
-    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4}; @q st.shared.v2.f64 [%0+16], {%5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]), "d"(v[2 % NW]), "d"(v[3 % NW]) : "memory");
+    if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f64 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]));
+    else if (NW == 2) asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]));
+    else asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4}; @q st.shared.v2.f64 [%0+16], {%5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]), "d"(v[2 % NW]), "d"(v[3 % NW]));
   }
   static __device__ __forceinline__ void load(unsigned a, double (&v)[NW]) {
-    if (NW == 1) asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a) : "memory");
+    if (NW == 1) asm("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a));
     else {
-      asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1 % NW]) : "r"(a) : "memory");
-      if (NW == 4) asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v[2 % NW]), "=d"(v[3 % NW]) : "r"(a) : "memory");
+      asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1 % NW]) : "r"(a));
+      if (NW == 4) asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v[2 % NW]), "=d"(v[3 % NW]) : "r"(a));
     }
   }
 };
@@ -377,14 +385,14 @@ __device__ __forceinline__ int bin_entry(const CountParams<T> &P, const BlockCtx
 // ---------------------------------------------------------------------------------------------
 // Shared-window (32-bit address) helpers for the drain: no generic-address arithmetic in the hot loop.
 __device__ __forceinline__ void red_shared_u32(unsigned a, bool p) {
-  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.u32 [%1], 1;}" ::"r"((int) p), "r"(a) : "memory");
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.u32 [%1], 1;}" ::"r"((int) p), "r"(a));
 }
 __device__ __forceinline__ void red_shared_f64(unsigned a, double v, bool p) {
-  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.f64 [%1], %2;}" ::"r"((int) p), "r"(a), "d"(v) : "memory");
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %0, 0; @q red.shared.add.f64 [%1], %2;}" ::"r"((int) p), "r"(a), "d"(v));
 }
 __device__ __forceinline__ int lds_u8(unsigned a, bool p) {
   unsigned v = 0;
-  asm volatile("{.reg .pred q; setp.ne.s32 q, %1, 0; @q ld.shared.u8 %0, [%2];}" : "+r"(v) : "r"((int) p), "r"(a) : "memory");
+  asm volatile("{.reg .pred q; setp.ne.s32 q, %1, 0; @q ld.shared.u8 %0, [%2];}" : "+r"(v) : "r"((int) p), "r"(a));
   return (int) v;
 }
 struct FastCtx { unsigned hist_s, stab_s, ptab_s, mutab_s; };
@@ -400,72 +408,152 @@ __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x);
 // move s by < 40 * 5e-7 and nmu*mu by < 255 * 5e-7, the reference's own roundings move nmu*mu by < 255 * 1.8e-7,
 // all far below 2^-12: a pair whose fraction bits are 0x000 or 0xFFF (within 2^-12 of a bin edge), d2 < EPS or
 // mu >= 1 is flagged and re-binned by the caller with the exact IEEE sequence (bin_entry).
-constexpr int kMantBias = 0x4B000000 >> 12;     // exponent bits of 2^23, shifted like the mantissa
-// Integer work is kept off the (half-rate) ALU pipe where possible: the +1 rides on an FFMA, the shifts are
-// IMAD.HI, the edge test is one AND per quantity, one IMAD and one compare.  A pair is flagged when the 12
-// fraction bits of 4096*x are in {0xFFF, 0, 1, 2} (x within [-2^-12, 3*2^-12) of an integer): this also
-// catches d2 < EPS (s < 3/4096) and mu >= 1 (nmu*mu within the band of nmu; it cannot exceed it by more).
+// Fast bins of a box / isotropic pair from ONE approximate reciprocal square root r = rsqrt(d2):
+//   s        = d2 * r            -> s bin  floor(s)   (floor(sqrt(floor(d2))) == floor(sqrt(d2)) exactly)
+//   nmu * mu = nmu * |dz| * r    -> mu bin floor(.)   (== floor(sqrt(floor(fl(fl(dz2/d2)*nmu^2)))) away from bin edges)
+// Both are computed scaled by 2^ks / 2^km (chosen on the host from ns / nmu) and truncated by adding 2^23 toward
+// zero: the mantissa then holds floor(2^k x) + 1 = bin * 2^k + k fraction bits (the +1 rides on the FFMA).
+// Error budget: rsqrt.approx 2^-22 rel. + two roundings move s by < ns * 3e-7; the same plus the reference's own
+// three roundings move nmu*mu by < nmu * 4.5e-7; the host picks 2^-ks >= 2.5 * ns * 3e-7 and 2^-km >= 2.2 * nmu * 4.5e-7.
+// A pair is flagged (re-binned with the exact IEEE sequence by the caller) when
+//   s  : fraction bits in {2^ks - 1, 0, 1, 2}  -> s within [-1, 3) / 2^ks of an edge; also catches d2 < EPS (s ~ 0)
+//   mu : fraction bits in {2^km - 1, 0}        -> nmu*mu within [-1, 1) / 2^km of an integer; also catches mu >= 1,
+//        since nmu*mu cannot exceed nmu by more than the error budget.
+// Integer work is kept off the half-rate ALU pipe where possible (IMAD.HI shifts, one IMAD + one compare for the test).
+// Returns the bin biased by bias_s + bias_m * ns, where bias = 0x4B000000 >> k; the caller folds it into the base address.
 template <int BIN>
-__device__ __forceinline__ int fast_bins(float d2, float dz, float nmu_f, int ns, bool &amb) {
+__device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale, const float mscale_nmu,
+                                         const unsigned int smask, const unsigned int mmask,
+                                         const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, bool &amb) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2 + 1e-30f));      // d2 = 0 (coincident points): finite r, s = 0 -> flagged
-  r *= 4096.0f;
-  const unsigned int us = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(d2, r, 1.0f), 8388608.0f));   // bias + floor(4096 s) + 1
-  unsigned int t = us & 0xFFCu;
-  int bin = (int) __umulhi(us, 1u << 20);       // us >> 12 = kMantBias + s bin
+  const unsigned int us = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(d2 * r, sscale, 1.0f), 8388608.0f));
+  unsigned int t = us & smask;
+  int bin = (int) __umulhi(us, sshift_mul);     // us >> ks
   if (BIN == BIN_SMU) {
-    const unsigned int um = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(fabsf(dz) * r, nmu_f, 1.0f), 8388608.0f));
-    t *= (um & 0xFFCu);
-    bin += (int) __umulhi(um, 1u << 20) * ns;   // + (kMantBias + mu bin) * ns
+    const unsigned int um = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(fabsf(dz) * r, mscale_nmu, 1.0f), 8388608.0f));
+    t *= (um & mmask);                          // (may wrap to 0: a spurious flag is harmless)
+    bin += (int) __umulhi(um, mshift_mul) * ns; // (um >> km) * ns
   }
+#if FCFC_ABLATE == 3            /* experiment: never re-bin exactly (results not exact) */
+  amb = false;
+#else
   amb = (t == 0u);
-  return bin - kMantBias * ((BIN == BIN_SMU) ? ns + 1 : 1);
+#endif
+  return bin;
 }
 
-// Drain of the fast variants (box or isotropic, shared-memory histogram, 8-bit integer tables, zero lower
-// bounds): every lane pops `rounds` entries off its stack (lanes with fewer idle), two per iteration,
-// branch-free apart from the rare exact re-binning.
+// Exact re-binning of a flagged pair, out of line (rare): keeps its registers and code out of the drain loop.
+// Tables are read from global memory (P.stab / P.mutab), which is fine at this frequency.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
+__device__ __noinline__ int rebin_exact(const CountParams<T> &P, T e0, T e1) {
+  BlockCtx<T> G;
+  G.hist_u = nullptr; G.hist_d = nullptr; G.blk_evals = nullptr;
+  G.stab = P.stab; G.ptab = P.ptab; G.mutab = P.mutab; G.s2bin = P.s2bin; G.pbin = P.pbin;
+  T e[NW], w;
+  e[0] = e0; e[1 % NW] = e1;
+  return bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
+}
+
+// Drain of the fast variants whose bins are computed (box (s,mu) or isotropic counts, integer tables that are
+// floor(sqrt(i)), zero lower bounds, shared-memory histogram): every lane pops `rounds` entries off its stack,
+// two per iteration.  While all lanes still have entries (FULL) nothing is predicated; the ragged tail, where
+// some lanes have run dry, predicates the histogram update.  Pairs flagged by fast_bins are re-binned exactly.
+template <class T, int BIN, bool WT, int NW, bool FULL, int NE>
+__device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, unsigned int &rp,
+                                                int k0, int k1, int mine, unsigned int &flagged) {
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  constexpr unsigned int HS = WT ? 8u : 4u;
+  const float sscale = P.fb_sscale, mscale = P.fb_mscale;
+  const unsigned int smask = P.fb_smask, mmask = P.fb_mmask, smul = 1u << (32 - P.fb_sshift), mmul = 1u << (32 - P.fb_mshift);
+  // NE independent entries per iteration and no data-dependent branch: flagged entries are only recorded
+  // (one bit per round) and re-binned after the loop.
+#pragma unroll 1
+  for (int k = k0; k < k1; k += NE, rp += NE * S) {
+    T e[NE][NW];
+#pragma unroll
+    for (int i = 0; i < NE; i++) QOps<T, NW>::load(rp + i * S, e[i]);   // slots above the old top hold stale entries: ignored
+    const unsigned int kbit = 1u << k;
+#pragma unroll
+    for (int i = 0; i < NE; i++) {
+      bool amb;
+      const int bin = fast_bins<BIN>(to_f32(e[i][0]), (BIN == BIN_SMU) ? to_f32(e[i][1 % NW]) : 0.0f, sscale, mscale, smask,
+                                     mmask, smul, mmul, P.ns, amb);
+      const bool h = FULL || (k + i < mine);
+      if (amb && h) flagged |= kbit << i;
+      const unsigned int addr = hist_adj + HS * (unsigned int) bin;
+#if FCFC_ABLATE == 2            /* experiment: binning without the histogram update */
+      if (bin == 0x7fffffff) red_shared_u32(addr, h && !amb);
+#else
+      if (WT) red_shared_f64(addr, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h && !amb);
+      else red_shared_u32(addr, h && !amb);
+#endif
+    }
+  }
+}
+
 template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
 __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
                                            LaneQueue<T, NW> &Q, int rounds) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  const float nmu_f = (float) (int) sqrtf((float) P.nmu2);
-  const int mine = min((int) (Q.fill_bytes() / S), rounds);     // entries this lane pops
+  const int mine = min((int) (Q.fill_bytes() / S), rounds);     // entries this lane pops (rounds <= 32)
   Q.top -= (unsigned int) mine * S;
   unsigned int rp = Q.top;
-  const bool table_math = P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt);
+  const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
+  const unsigned int hist_adj = F.hist_s - (WT ? 8u : 4u) * (unsigned int) bias;
+  const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;  // rounds in which every lane still has four entries
+#if FCFC_ABLATE == 1            /* experiment: pop without binning */
+  if (P.ns > 0) return;
+#endif
+  unsigned int flagged = 0;     // bit k: the entry of round k must be re-binned exactly
+  drain_fast_loop<T, BIN, WT, NW, true, 4>(P, hist_adj, rp, 0, nfull, mine, flagged);
+  drain_fast_loop<T, BIN, WT, NW, false, 2>(P, hist_adj, rp, nfull, rounds, mine, flagged);
+  while (__any_sync(0xffffffffu, flagged != 0)) {               // rare: a few entries per thousand
+    if (flagged) {
+      const int k = __ffs((int) flagged) - 1;
+      flagged &= flagged - 1;
+      T e[NW];
+      QOps<T, NW>::load(Q.top + (unsigned int) k * S, e);
+      const int b = rebin_exact<T, BIN, BOX, WT, ARITH, NW>(P, e[0], e[1 % NW]);
+      if (b >= 0) {
+        if (WT) red_shared_f64(F.hist_s + 8u * (unsigned int) b, (double) e[(BIN == BIN_ISO) ? 1 % NW : 2 % NW], true);
+        else red_shared_u32(F.hist_s + 4u * (unsigned int) b, true);
+      }
+    }
+  }
+}
+
+// Drain of the fast variants that look their bins up: box (s_perp, pi), or integer tables that are not
+// floor(sqrt(i)).  Exact by construction (truncation + table), predicated shared-memory loads.
+template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
+__device__ __forceinline__ void drain_lut(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
+                                          LaneQueue<T, NW> &Q, int rounds) {
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  const int mine = min((int) (Q.fill_bytes() / S), rounds);
+  Q.top -= (unsigned int) mine * S;
+  unsigned int rp = Q.top;
 #pragma unroll 1
   for (int k = 0; k < rounds; k += 2, rp += 2 * S) {
-    const bool h0 = k < mine, h1 = k + 1 < mine;
     T e[2][NW];
     QOps<T, NW>::load(rp, e[0]);
-    QOps<T, NW>::load(rp + S, e[1]);            // slots above the old top hold stale (zeroed or older) entries: ignored
-    int bin[2]; bool amb[2]; T w[2];
+    QOps<T, NW>::load(rp + S, e[1]);
 #pragma unroll
     for (int i = 0; i < 2; i++) {
-      const bool h = i ? h1 : h0;
-      if (BIN != BIN_SPI) {
-        bin[i] = fast_bins<BIN>(to_f32(e[i][0]), (BIN == BIN_SMU) ? to_f32(e[i][1 % NW]) : 0.0f, nmu_f, P.ns, amb[i]);
-        amb[i] = (amb[i] || !table_math) && h;
-      } else {          // box (s_perp, pi): two integer-table lookups (or identity / sqrt when the tables are that)
+      bool h = k + i < mine;
+      int bin;
+      if (BIN == BIN_SPI) {
         int sb, pb = trunc_pos(e[i][1 % NW]);
         const int fl = trunc_pos(e[i][0]);
         if (P.stab_is_sqrt) sb = isqrt_small(fl); else sb = lds_u8(F.stab_s + (unsigned) fl, h);
         if (!P.ptab_is_ident) pb = lds_u8(F.ptab_s + (unsigned) pb, h);
-        bin[i] = sb + pb * P.ns; amb[i] = false;
+        bin = sb + pb * P.ns;
+      } else {
+        T ww;
+        bin = h ? bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, C, e[i], ww) : -1;
+        h = bin >= 0;
       }
-      w[i] = WT ? e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW] : (T) 1;
-    }
-    if (BIN != BIN_SPI && __any_sync(0xffffffffu, amb[0] || amb[1])) {
-#pragma unroll
-      for (int i = 0; i < 2; i++)
-        if (amb[i]) { T ww; bin[i] = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, C, e[i], ww); }
-    }
-#pragma unroll
-    for (int i = 0; i < 2; i++) {
-      const bool ok = (i ? h1 : h0) && bin[i] >= 0;
-      if (WT) red_shared_f64(F.hist_s + 8u * (unsigned) bin[i], (double) w[i], ok);
-      else red_shared_u32(F.hist_s + 4u * (unsigned) bin[i], ok);
+      if (WT) red_shared_f64(F.hist_s + 8u * (unsigned) bin, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h);
+      else red_shared_u32(F.hist_s + 4u * (unsigned) bin, h);
     }
   }
 }
@@ -496,10 +584,12 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
   const int mx = (int) (__reduce_max_sync(0xffffffffu, Q.fill_bytes()) / S);
   if (mx + need <= P.qdepth - 1) return mx;
-  const int rounds = mx - keep;
-  if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
-  else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
-  return max(keep, 0);
+  const int rounds = min(mx - keep, 32);        // (the fast drain records flagged rounds in a 32-bit mask)
+  if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) {
+    if (BIN != BIN_SPI && P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
+    else drain_lut<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
+  } else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
+  return mx - rounds;
 }
 
 // One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane,
@@ -535,7 +625,7 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
 }
 
 template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int RMAX>
-__global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const CountParams<T> P) {
+__global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const __grid_constant__ CountParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int kThreads = BlockShape<T>::kThreads, kWarpsPerBlock = BlockShape<T>::kWarps;
   constexpr int NW = QFmt<BIN, BOX, WT>::NW;
@@ -550,7 +640,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   T *s_s2bin = reinterpret_cast<T *>(smem + pl.off_s2bin), *s_pbin = reinterpret_cast<T *>(smem + pl.off_pbin);
   int4 *s_rows = reinterpret_cast<int4 *>(smem + pl.off_rows);
   C.stab = s_stab; C.ptab = s_ptab; C.mutab = s_mutab; C.s2bin = s_s2bin; C.pbin = s_pbin;
-  if (GENERIC && P.tabs_global) { C.stab = P.stab; C.ptab = P.ptab; C.mutab = P.mutab; }     // generic variant only
+  if (P.tabs_global) { C.stab = P.stab; C.ptab = P.ptab; C.mutab = P.mutab; }     // generic variant, or fast variant whose tables are computed
   unsigned int *s_blk_evals = reinterpret_cast<unsigned int *>(smem + pl.off_misc);
   C.blk_evals = s_blk_evals;
 
@@ -708,7 +798,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     }
   }
   // whatever is still queued
-  drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, P.qdepth, 0);
+  while (drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, P.qdepth, 0) > 0) {}
 
   // ---- block epilogue: flush the histogram ----
   __syncthreads();

@@ -502,30 +502,6 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   int dev = 0; cudaGetDevice(&dev);
   int smem_max = 0; cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   const int nmutab = (bintype == BIN_SMU) ? nmu * nmu : 0;
-  // accepted-pair queues: the deepest power-of-two depth that fits next to the histogram and tables
-  const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
-  auto plan = [&](bool sh, int depth, bool tg) {
-    return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg)
-                  : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
-  };
-  int qdepth_max = 64;
-  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd));
-  // preference order: everything in shared memory with deep queues > tables in global memory >
-  // shallow queues > histogram in global memory (large tables / histograms are rare)
-  SmemPlan pl; int depth = 0; bool tabs_global = false; v.smem_hist = true;
-  const struct { bool sh, tg; int dmin; } tries[] = {{true, false, 16}, {true, true, 16}, {true, false, 8}, {true, true, 8},
-                                                     {false, false, 16}, {false, true, 8}};
-  for (auto &t : tries) {
-    for (int d = qdepth_max; d >= t.dmin && !depth; d >>= 1) {
-      pl = plan(t.sh, d, t.tg);
-      if (pl.total + 1024 <= smem_max) { depth = d; v.smem_hist = t.sh; tabs_global = t.tg; }
-    }
-    if (depth) break;
-  }
-  if (!depth) { cudaFree(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
-  P.tabs_global = tabs_global;
-  if (tabs_global) v.generic = true;            // only the generic variant reads tables through global pointers
-  if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   // tables that are pure functions of the index are computed in registers instead of looked up
   {
     auto is_sqrt = [](const void *tab, int width, long n) {
@@ -545,7 +521,43 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
       for (long i = 0; i < nptab; i++) { long vv = b->pwidth ? ((const uint16_t *) b->ptab)[i] : ((const uint8_t *) b->ptab)[i]; if (vv != i) P.ptab_is_ident = 0; }
     }
     if (getenv("FCFC_GPU_NO_TABLE_MATH")) P.mu_is_sqrt = P.stab_is_sqrt = P.ptab_is_ident = 0;
+    // fixed-point scales of the fast bins (count_kernel.cuh, fast_bins): the flag band 2^-k must cover the error
+    // budget with a factor >= 2 to spare, and bin * 2^k must stay below 2^23
+    auto pick = [](double need, int nbin) { int k = 20; while (k > 4 && (std::ldexp(1.0, -k) < need || (double) (nbin + 2) * std::ldexp(1.0, k) >= 8388608.0)) k--; return k; };
+    const int ks = pick(2.5 * 3e-7 * (ns + 1), ns), km = pick(2.2 * 4.5e-7 * (nmu + 1), nmu);
+    P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
+    P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
+    if (ks < 6 || km < 6) P.stab_is_sqrt = 0;   // too many bins for the fixed-point trick: use the exact path
   }
+  // accepted-pair queues: the deepest power-of-two depth that fits next to the histogram and tables
+  const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
+  auto plan = [&](bool sh, int depth, bool tg) {
+    return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg)
+                  : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
+  };
+  int qdepth_max = 64;
+  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd));
+  // preference order: everything in shared memory with deep queues > tables in global memory >
+  // shallow queues > histogram in global memory (large tables / histograms are rare)
+  SmemPlan pl; int depth = 0; bool tabs_global = false; v.smem_hist = true;
+  const struct { bool sh, tg; int dmin; } tries[] = {{true, false, 16}, {true, true, 16}, {true, false, 8}, {true, true, 8},
+                                                     {false, false, 16}, {false, true, 8}};
+  // fast variants whose s and mu bins are computed never read the tables in the hot loop: leave them in
+  // global memory (the exact re-binning of flagged pairs reads them there) and give the space to the stacks
+  const bool fast_variant = !generic && !getenv("FCFC_GPU_FORCE_GENERIC") && (b->periodic || bintype == BIN_ISO);
+  const bool tables_unused = fast_variant && P.stab_is_sqrt && ((bintype == BIN_SMU && P.mu_is_sqrt) || bintype == BIN_ISO);
+  for (auto &t : tries) {
+    if (tables_unused && !t.tg && t.sh) continue;       // computed bins: deeper stacks beat resident tables
+    for (int d = qdepth_max; d >= t.dmin && !depth; d >>= 1) {
+      pl = plan(t.sh, d, t.tg);
+      if (pl.total + 1024 <= smem_max) { depth = d; v.smem_hist = t.sh; tabs_global = t.tg; }
+    }
+    if (depth) break;
+  }
+  if (!depth) { cudaFree(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  P.tabs_global = tabs_global;
+  if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
+  if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   P.qdepth = depth;
   cudaEventRecord(ev1);
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
