@@ -55,6 +55,62 @@ static int ensure_init() {
 }
 
 // ------------------------------------------------------------------------------------------
+// Device memory pool.  cudaMalloc / cudaFree cost milliseconds and synchronise the device; a count step
+// allocates a dozen buffers of recurring sizes (catalogue columns, sort scratch, cell tables), so freed
+// blocks are kept and handed out again (first fit within 2x).  Everything is returned by fcfc_gpu_finalize.
+struct PoolBlock { void *p; size_t bytes; int dev; };
+static std::vector<PoolBlock> g_pool_free, g_pool_used;
+static size_t g_pool_cached = 0;
+static const size_t kPoolMaxCached = (size_t) 48 << 30;
+
+static cudaError_t pool_alloc(void **out, size_t bytes) {
+  int dev = 0; cudaGetDevice(&dev);
+  bytes = (bytes + 511) & ~(size_t) 511;
+  if (bytes == 0) bytes = 512;
+  size_t best = (size_t) -1;
+  for (size_t i = 0; i < g_pool_free.size(); i++)
+    if (g_pool_free[i].dev == dev && g_pool_free[i].bytes >= bytes && g_pool_free[i].bytes <= 2 * bytes &&
+        (best == (size_t) -1 || g_pool_free[i].bytes < g_pool_free[best].bytes)) best = i;
+  if (best != (size_t) -1) {
+    PoolBlock b = g_pool_free[best];
+    g_pool_free.erase(g_pool_free.begin() + best);
+    g_pool_cached -= b.bytes;
+    g_pool_used.push_back(b);
+    *out = b.p;
+    return cudaSuccess;
+  }
+  void *p = nullptr;
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess) {               // out of memory: give the cache back and retry once
+    cudaGetLastError();
+    for (auto &b : g_pool_free) cudaFree(b.p);
+    g_pool_free.clear(); g_pool_cached = 0;
+    e = cudaMalloc(&p, bytes);
+    if (e != cudaSuccess) return e;
+  }
+  g_pool_used.push_back({p, bytes, dev});
+  *out = p;
+  return cudaSuccess;
+}
+static void pool_free(void *p) {
+  if (!p) return;
+  for (size_t i = 0; i < g_pool_used.size(); i++)
+    if (g_pool_used[i].p == p) {
+      PoolBlock b = g_pool_used[i];
+      g_pool_used.erase(g_pool_used.begin() + i);
+      if (g_pool_cached + b.bytes > kPoolMaxCached) { cudaFree(b.p); return; }
+      g_pool_free.push_back(b); g_pool_cached += b.bytes;
+      return;
+    }
+  cudaFree(p);
+}
+static void pool_release_all() {
+  for (auto &b : g_pool_free) cudaFree(b.p);
+  g_pool_free.clear(); g_pool_cached = 0;
+}
+template <class P> static cudaError_t pool_alloc(P **out, size_t bytes) { return pool_alloc(reinterpret_cast<void **>(out), bytes); }
+
+// ------------------------------------------------------------------------------------------
 // cell grid
 struct Grid {
   int nc[3] = {1, 1, 1};
@@ -79,7 +135,7 @@ template <class T> struct Sorted {
   int *item_cell = nullptr, *item_off = nullptr, *item_cnt = nullptr;
   int nitem = 0;
   void release() {
-    cudaFree(pos); cudaFree(w); cudaFree(cell_start); cudaFree(item_cell); cudaFree(item_off); cudaFree(item_cnt);
+    pool_free(pos); pool_free(w); pool_free(cell_start); pool_free(item_cell); pool_free(item_off); pool_free(item_cnt);
     pos = nullptr; w = nullptr; cell_start = nullptr; item_cell = item_off = item_cnt = nullptr;
     valid = false; nitem = 0;
   }
@@ -229,14 +285,14 @@ static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool nee
   cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
   unsigned int *key = nullptr, *key2 = nullptr; int *idx = nullptr, *idx2 = nullptr, *err = nullptr;
   int *ntile = nullptr, *tile_off = nullptr; void *tmp = nullptr;
-  auto cleanup = [&]() { cudaFree(key); cudaFree(key2); cudaFree(idx); cudaFree(idx2); cudaFree(err); cudaFree(ntile); cudaFree(tile_off); cudaFree(tmp); };
+  auto cleanup = [&]() { pool_free(key); pool_free(key2); pool_free(idx); pool_free(idx2); pool_free(err); pool_free(ntile); pool_free(tile_off); pool_free(tmp); };
 #define TRY_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err("%s: %s", #x, cudaGetErrorString(e_)); cudaGetLastError(); cleanup(); S.release(); return FCFC_GPU_ERR_TREE; } } while (0)
   const size_t nn = n ? n : 1;
-  TRY_(cudaMalloc(&key, nn * 4)); TRY_(cudaMalloc(&key2, nn * 4)); TRY_(cudaMalloc(&idx, nn * 4)); TRY_(cudaMalloc(&idx2, nn * 4));
-  TRY_(cudaMalloc(&err, 4)); TRY_(cudaMemset(err, 0, 4));
-  TRY_(cudaMalloc(&S.pos, nn * sizeof(Vec4<T>)));
-  if (need_w) TRY_(cudaMalloc(&S.w, nn * sizeof(T)));
-  TRY_(cudaMalloc(&S.cell_start, (ncell + 1) * sizeof(int)));
+  TRY_(pool_alloc(&key, nn * 4)); TRY_(pool_alloc(&key2, nn * 4)); TRY_(pool_alloc(&idx, nn * 4)); TRY_(pool_alloc(&idx2, nn * 4));
+  TRY_(pool_alloc(&err, 4)); TRY_(cudaMemset(err, 0, 4));
+  TRY_(pool_alloc(&S.pos, nn * sizeof(Vec4<T>)));
+  if (need_w) TRY_(pool_alloc(&S.w, nn * sizeof(T)));
+  TRY_(pool_alloc(&S.cell_start, (ncell + 1) * sizeof(int)));
   const int nb = (n + 255) / 256;
   if (n) {
     cellid_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z, n, g, key, idx, err);
@@ -244,7 +300,7 @@ static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool nee
     int bits = 1; while ((1ll << bits) < ncell) bits++;
     size_t tb = 0;
     TRY_(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, idx, idx2, n, 0, bits));
-    TRY_(cudaMalloc(&tmp, tb ? tb : 1));
+    TRY_(pool_alloc(&tmp, tb ? tb : 1));
     TRY_(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, idx, idx2, n, 0, bits));
     gather_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z,
                                   cat->has_s ? (const T *) cat->s : nullptr, cat->has_w ? (const T *) cat->w : nullptr,
@@ -260,19 +316,19 @@ static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool nee
     cleanup(); S.release(); return FCFC_GPU_ERR_DATA;
   }
   // work items
-  TRY_(cudaMalloc(&ntile, (ncell + 1) * sizeof(int))); TRY_(cudaMalloc(&tile_off, (ncell + 1) * sizeof(int)));
+  TRY_(pool_alloc(&ntile, (ncell + 1) * sizeof(int))); TRY_(pool_alloc(&tile_off, (ncell + 1) * sizeof(int)));
   TRY_(cudaMemset(ntile, 0, (ncell + 1) * sizeof(int)));
   ntile_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, (int) ncell, tile, ntile);
-  cudaFree(tmp); tmp = nullptr;
+  pool_free(tmp); tmp = nullptr;
   size_t tb = 0;
   TRY_(cub::DeviceScan::ExclusiveSum(nullptr, tb, ntile, tile_off, (int) ncell + 1));
-  TRY_(cudaMalloc(&tmp, tb ? tb : 1));
+  TRY_(pool_alloc(&tmp, tb ? tb : 1));
   TRY_(cub::DeviceScan::ExclusiveSum(tmp, tb, ntile, tile_off, (int) ncell + 1));
   int nitem = 0;
   TRY_(cudaMemcpy(&nitem, tile_off + ncell, 4, cudaMemcpyDeviceToHost));
   S.nitem = nitem;
   const size_t ni = nitem ? nitem : 1;
-  TRY_(cudaMalloc(&S.item_cell, ni * 4)); TRY_(cudaMalloc(&S.item_off, ni * 4)); TRY_(cudaMalloc(&S.item_cnt, ni * 4));
+  TRY_(pool_alloc(&S.item_cell, ni * 4)); TRY_(pool_alloc(&S.item_off, ni * 4)); TRY_(pool_alloc(&S.item_cnt, ni * 4));
   items_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, tile_off, (int) ncell, tile, S.item_cell, S.item_off, S.item_cnt);
   g_stats.kernel_launches += 3;
   TRY_(cudaGetLastError());
@@ -460,7 +516,7 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   if (sz_pb) memcpy(&hbuf[o_pb], pbin, sz_pb);
   if (sz_rows) memcpy(&hbuf[o_rows], rows.data(), sz_rows);
   unsigned char *dbuf = nullptr;
-  CUDA_TRY(cudaMalloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool_alloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(cudaMemcpy(dbuf, hbuf.data(), o_end, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
 
   // ---- kernel parameters ----
@@ -554,7 +610,7 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
     }
     if (depth) break;
   }
-  if (!depth) { cudaFree(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  if (!depth) { pool_free(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
@@ -564,10 +620,10 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(ev2);
-  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); cudaFree(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); pool_free(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   // ---- results ----
   cudaError_t ce = cudaMemcpy(withwt ? (void *) cnt_d : (void *) cnt_i, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToHost);
-  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); cudaFree(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); pool_free(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   if (dev_hist) cudaMemcpy(dev_hist, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToDevice);
   unsigned long long ev = 0;
   cudaMemcpy(&ev, dbuf + o_cnt + 8, 8, cudaMemcpyDeviceToHost);
@@ -580,7 +636,7 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];
   g_stats.nitem = P.item_end - P.item_begin;
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
-  cudaFree(dbuf);
+  pool_free(dbuf);
   return 0;
 }
 
@@ -620,30 +676,30 @@ extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
   return (int) g_ctx.devices.size();
 }
 
-extern "C" void fcfc_gpu_finalize(void) { g_ctx.ready = false; g_ctx.devices.clear(); }
+extern "C" void fcfc_gpu_finalize(void) { pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear(); }
 
 template <class T>
 static int catalog_upload(fcfc_gpu_catalog *c, const void *x, const void *y, const void *z, const void *s, const void *w,
                           double rescale, int sumsq) {
   const size_t n = c->n, bytes = (n ? n : 1) * sizeof(T);
-  CUDA_TRY(cudaMalloc(&c->x, bytes), FCFC_GPU_ERR_MEMORY);
-  CUDA_TRY(cudaMalloc(&c->y, bytes), FCFC_GPU_ERR_MEMORY);
-  CUDA_TRY(cudaMalloc(&c->z, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool_alloc(&c->x, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool_alloc(&c->y, bytes), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool_alloc(&c->z, bytes), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(cudaMemcpy(c->x, x, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   CUDA_TRY(cudaMemcpy(c->y, y, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   CUDA_TRY(cudaMemcpy(c->z, z, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   c->has_s = (s != nullptr) || sumsq >= 0;
   if (c->has_s) {
-    CUDA_TRY(cudaMalloc(&c->s, bytes), FCFC_GPU_ERR_MEMORY);
+    CUDA_TRY(pool_alloc(&c->s, bytes), FCFC_GPU_ERR_MEMORY);
     if (s) CUDA_TRY(cudaMemcpy(c->s, s, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   }
   c->has_w = w != nullptr;
   if (w) {
-    CUDA_TRY(cudaMalloc(&c->w, bytes), FCFC_GPU_ERR_MEMORY);
+    CUDA_TRY(pool_alloc(&c->w, bytes), FCFC_GPU_ERR_MEMORY);
     CUDA_TRY(cudaMemcpy(c->w, w, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   }
   unsigned long long *stats = nullptr; double *wsum = nullptr;
-  CUDA_TRY(cudaMalloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool_alloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
   wsum = reinterpret_cast<double *>(stats + 8);
   unsigned long long init[9];
   for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
@@ -657,7 +713,7 @@ static int catalog_upload(fcfc_gpu_catalog *c, const void *x, const void *y, con
   }
   unsigned long long out[9];
   CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
-  cudaFree(stats);
+  pool_free(stats);
   if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
   for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
   c->smax = n ? dec_f64(out[6]) : 0;
@@ -682,7 +738,7 @@ extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *
 
 extern "C" void fcfc_gpu_catalog_destroy(fcfc_gpu_catalog *c) {
   if (!c) return;
-  cudaFree(c->x); cudaFree(c->y); cudaFree(c->z); cudaFree(c->s); cudaFree(c->w);
+  pool_free(c->x); pool_free(c->y); pool_free(c->z); pool_free(c->s); pool_free(c->w);
   c->sf.release(); c->sd.release();
   delete c;
 }
