@@ -271,8 +271,16 @@ def main():
     k_ms = float(np.mean(kern_ms))
     evals_per_launch = evals["n"] / args.steps
     achieved = evals_per_launch / (k_ms * 1e-3) * 6.0 * 1e-12           # T FP32 lane-instructions/s of algorithmic work
+    traffic = None
+    try:        # DRAM bytes of one launch of this workload's count kernel, from the committed ncu --set full capture
+        t = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get(args.workload)
+        if t and world == 1 and args.prec == "float":
+            traffic = t["dram_bytes_read"] + t["dram_bytes_write"]
+    except Exception:
+        pass
     roofline = {"bound": "fp32_issue", "achieved": achieved, "peak": peak_instr * 1e-12, "unit": "T FP32 instr/s (6 per pair evaluation)",
-                "frac": achieved / (peak_instr * 1e-12), "traffic": None, "kernel": "fcfc::count_kernel", "kernel_ms": k_ms,
+                "frac": achieved / (peak_instr * 1e-12), "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
+                "algorithmic_bytes": 16 * wl["n"], "kernel": "fcfc::count_kernel", "kernel_ms": k_ms,
                 "peak_source": "measured live: FFMA stream on all SMs (fcfc_gpu_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
                 "evals_per_sec_kernel": evals_per_launch / (k_ms * 1e-3), "r_eval_peak": peak_instr / 6.0}
     kappa = evals["n"] / args.steps * world / max(pairs_in, 1) if world == 1 else total_evals / args.steps / max(pairs_in, 1)
