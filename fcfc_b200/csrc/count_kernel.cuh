@@ -107,6 +107,7 @@ template <class T> struct CountParams {
   const T *s2bin; const T *pbin;
   int isauto;
   int tabs_global;                      // lookup tables too large for shared memory: read them from global memory
+  int hist_copies;                      // weighted shared-memory histogram: 32 lane-private copies (few bins) or 1
   int qdepth;                           // entries per lane of the accepted-pair queues (power of two)
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
@@ -125,12 +126,12 @@ template <int BIN, bool BOX, bool WT> struct QFmt {
 
 template <class T, bool WT>
 __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, int nptab_bytes, int nmutab_bytes,
-                                                   int ns, int np, int nrows, bool smem_hist, int qwords, int qdepth, bool tabs_global) {
+                                                   int ns, int np, int nrows, bool smem_hist, int qwords, int qdepth, bool tabs_global, int hist_copies = 1) {
   constexpr int kWarpsPerBlock = BlockShape<T>::kWarps;
   SmemPlan p;
   int o = 0;
   auto al = [](int v) { return (v + 15) & ~15; };
-  p.off_hist = o; o += smem_hist ? al(ntot * (WT ? 8 : 4)) : 0;
+  p.off_hist = o; o += smem_hist ? al(ntot * (WT ? 8 * hist_copies : 4)) : 0;
   p.off_stab = o; o += tabs_global ? 0 : al(nstab_bytes);
   p.off_ptab = o; o += tabs_global ? 0 : al(nptab_bytes);
   p.off_mutab = o; o += tabs_global ? 0 : al(nmutab_bytes);
@@ -151,6 +152,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, in
 template <class T> struct BlockCtx {
   unsigned int *hist_u;         // shared or global 32/64-bit counters (unweighted)
   double *hist_d;               // weighted sums
+  int hmul, hoff;               // weighted bin -> slot: bin * hmul + hoff (lane-private copies when bins are few)
   const uint8_t *stab, *ptab, *mutab;
   const T *s2bin, *pbin;
   unsigned int *blk_evals;      // shared overflow accounting
@@ -254,7 +256,7 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
 template <class T, bool WT, bool SMEMHIST>
 __device__ __forceinline__ void hist_add(const BlockCtx<T> &C, int bin, T w) {
   if (WT) {
-    atomicAdd(&C.hist_d[bin], (double) w);      // product formed in `real`, summed in double: metric_common.c:216-231
+    atomicAdd(&C.hist_d[bin * C.hmul + C.hoff], (double) w);    // product formed in `real`, summed in double: metric_common.c:216-231
   } else if (SMEMHIST) {
     atomicAdd(&C.hist_u[bin], 1u);
   } else {
@@ -395,7 +397,7 @@ __device__ __forceinline__ int lds_u8(unsigned a, bool p) {
   asm volatile("{.reg .pred q; setp.ne.s32 q, %1, 0; @q ld.shared.u8 %0, [%2];}" : "+r"(v) : "r"((int) p), "r"(a));
   return (int) v;
 }
-struct FastCtx { unsigned hist_s, stab_s, ptab_s, mutab_s; };
+struct FastCtx { unsigned hist_s, stab_s, ptab_s, mutab_s; unsigned hstride, hlane; };   // weighted: bytes per bin, byte offset of this lane's copy
 
 __device__ __forceinline__ float to_f32(float x) { return x; }
 __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x); }
@@ -460,10 +462,9 @@ __device__ __noinline__ int rebin_exact(const CountParams<T> &P, T e0, T e1) {
 // two per iteration.  While all lanes still have entries (FULL) nothing is predicated; the ragged tail, where
 // some lanes have run dry, predicates the histogram update.  Pairs flagged by fast_bins are re-binned exactly.
 template <class T, int BIN, bool WT, int NW, bool FULL, int NE>
-__device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, unsigned int &rp,
+__device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, const unsigned int HS, unsigned int &rp,
                                                 int k0, int k1, int mine, unsigned int &flagged) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  constexpr unsigned int HS = WT ? 8u : 4u;
   const float sscale = P.fb_sscale, mscale = P.fb_mscale;
   const unsigned int smask = P.fb_smask, mmask = P.fb_mmask, smul = 1u << (32 - P.fb_sshift), mmul = 1u << (32 - P.fb_mshift);
   // NE independent entries per iteration and no data-dependent branch: flagged entries are only recorded
@@ -500,14 +501,15 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
   Q.top -= (unsigned int) mine * S;
   unsigned int rp = Q.top;
   const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
-  const unsigned int hist_adj = F.hist_s - (WT ? 8u : 4u) * (unsigned int) bias;
+  const unsigned int hs = WT ? F.hstride : 4u;
+  const unsigned int hist_adj = F.hist_s + (WT ? F.hlane : 0u) - hs * (unsigned int) bias;
   const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;  // rounds in which every lane still has four entries
 #if FCFC_ABLATE == 1            /* experiment: pop without binning */
   if (P.ns > 0) return;
 #endif
   unsigned int flagged = 0;     // bit k: the entry of round k must be re-binned exactly
-  drain_fast_loop<T, BIN, WT, NW, true, 4>(P, hist_adj, rp, 0, nfull, mine, flagged);
-  drain_fast_loop<T, BIN, WT, NW, false, 2>(P, hist_adj, rp, nfull, rounds, mine, flagged);
+  drain_fast_loop<T, BIN, WT, NW, true, 4>(P, hist_adj, hs, rp, 0, nfull, mine, flagged);
+  drain_fast_loop<T, BIN, WT, NW, false, 2>(P, hist_adj, hs, rp, nfull, rounds, mine, flagged);
   while (__any_sync(0xffffffffu, flagged != 0)) {               // rare: a few entries per thousand
     if (flagged) {
       const int k = __ffs((int) flagged) - 1;
@@ -516,7 +518,7 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
       QOps<T, NW>::load(Q.top + (unsigned int) k * S, e);
       const int b = rebin_exact<T, BIN, BOX, WT, ARITH, NW>(P, e[0], e[1 % NW]);
       if (b >= 0) {
-        if (WT) red_shared_f64(F.hist_s + 8u * (unsigned int) b, (double) e[(BIN == BIN_ISO) ? 1 % NW : 2 % NW], true);
+        if (WT) red_shared_f64(F.hist_s + F.hlane + F.hstride * (unsigned int) b, (double) e[(BIN == BIN_ISO) ? 1 % NW : 2 % NW], true);
         else red_shared_u32(F.hist_s + 4u * (unsigned int) b, true);
       }
     }
@@ -552,7 +554,7 @@ __device__ __forceinline__ void drain_lut(const CountParams<T> &P, const BlockCt
         bin = h ? bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, C, e[i], ww) : -1;
         h = bin >= 0;
       }
-      if (WT) red_shared_f64(F.hist_s + 8u * (unsigned) bin, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h);
+      if (WT) red_shared_f64(F.hist_s + F.hlane + F.hstride * (unsigned) bin, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h);
       else red_shared_u32(F.hist_s + 4u * (unsigned) bin, h);
     }
   }
@@ -632,10 +634,12 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
   const SmemPlan pl = make_smem_plan<T, WT>(P.ntot, P.nstab * (P.swidth ? 2 : 1), P.nptab * (P.pwidth ? 2 : 1),
-                                            nmutab, P.ns, P.np, P.nrows, SMEMHIST, NW, P.qdepth, P.tabs_global != 0);
+                                            nmutab, P.ns, P.np, P.nrows, SMEMHIST, NW, P.qdepth, P.tabs_global != 0, WT ? P.hist_copies : 1);
   BlockCtx<T> C;
   C.hist_u = SMEMHIST ? reinterpret_cast<unsigned int *>(smem + pl.off_hist) : reinterpret_cast<unsigned int *>(P.ghist_i);
   C.hist_d = SMEMHIST ? reinterpret_cast<double *>(smem + pl.off_hist) : P.ghist_d;
+  const int hcopies = (WT && SMEMHIST) ? P.hist_copies : 1;
+  C.hmul = hcopies; C.hoff = (hcopies > 1) ? lane : 0;
   uint8_t *s_stab = smem + pl.off_stab, *s_ptab = smem + pl.off_ptab, *s_mutab = smem + pl.off_mutab;
   T *s_s2bin = reinterpret_cast<T *>(smem + pl.off_s2bin), *s_pbin = reinterpret_cast<T *>(smem + pl.off_pbin);
   int4 *s_rows = reinterpret_cast<int4 *>(smem + pl.off_rows);
@@ -646,7 +650,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
 
   // ---- block prologue: zero the histogram, stage tables / edges / stencil rows ----
   if (SMEMHIST) {
-    if (WT) for (int i = threadIdx.x; i < P.ntot; i += kThreads) C.hist_d[i] = 0.0;
+    if (WT) for (int i = threadIdx.x; i < P.ntot * hcopies; i += kThreads) C.hist_d[i] = 0.0;
     else for (int i = threadIdx.x; i < P.ntot; i += kThreads) C.hist_u[i] = 0u;
   }
   if (!P.tabs_global) {
@@ -664,6 +668,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   __syncthreads();
   FastCtx F;
   F.hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
+  F.hstride = 8u * (unsigned int) hcopies; F.hlane = (hcopies > 1) ? 8u * (unsigned int) lane : 0u;
   F.stab_s = (unsigned int) __cvta_generic_to_shared(s_stab);
   F.ptab_s = (unsigned int) __cvta_generic_to_shared(s_ptab);
   F.mutab_s = (unsigned int) __cvta_generic_to_shared(s_mutab);
@@ -804,7 +809,11 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   __syncthreads();
   if (SMEMHIST) {
     if (WT) {
-      for (int i = threadIdx.x; i < P.ntot; i += kThreads) { double v = C.hist_d[i]; if (v != 0.0) atomicAdd(&P.ghist_d[i], v); }
+      for (int i = threadIdx.x; i < P.ntot; i += kThreads) {
+        double v = 0.0;
+        for (int c = 0; c < hcopies; c++) v += C.hist_d[i * hcopies + c];
+        if (v != 0.0) atomicAdd(&P.ghist_d[i], v);
+      }
     } else {
       for (int i = threadIdx.x; i < P.ntot; i += kThreads) { unsigned int v = C.hist_u[i]; if (v) atomicAdd(&P.ghist_i[i], (unsigned long long) v); }
     }

@@ -587,8 +587,12 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   }
   // accepted-pair queues: the deepest power-of-two depth that fits next to the histogram and tables
   const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
+  // weighted sums with few bins: 32 lane-private copies of the shared histogram, so that the FP64 (CAS) atomics
+  // of the lanes of a warp never collide on a bin
+  const int hist_copies = (withwt && ntot <= 256 && !getenv("FCFC_GPU_NO_HIST_COPIES")) ? 32 : 1;
+  P.hist_copies = hist_copies;
   auto plan = [&](bool sh, int depth, bool tg) {
-    return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg)
+    return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg, hist_copies)
                   : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
   };
   int qdepth_max = 64;
@@ -602,7 +606,9 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   // global memory (the exact re-binning of flagged pairs reads them there) and give the space to the stacks
   const bool fast_variant = !generic && !getenv("FCFC_GPU_FORCE_GENERIC") && (b->periodic || bintype == BIN_ISO);
   const bool tables_unused = fast_variant && P.stab_is_sqrt && ((bintype == BIN_SMU && P.mu_is_sqrt) || bintype == BIN_ISO);
+  const bool force_ghist = getenv("FCFC_GPU_GLOBAL_HIST") != nullptr;       // experiment hook
   for (auto &t : tries) {
+    if (force_ghist && t.sh) continue;
     if (tables_unused && !t.tg && t.sh) continue;       // computed bins: deeper stacks beat resident tables
     for (int d = qdepth_max; d >= t.dmin && !depth; d >>= 1) {
       pl = plan(t.sh, d, t.tg);
