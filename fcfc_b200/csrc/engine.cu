@@ -216,19 +216,27 @@ __global__ void prep_kernel(T *x, T *y, T *z, T *s, size_t n, T rescale, int do_
 
 // cell id of every point (double arithmetic so that float and double catalogues bin identically)
 template <class T>
-__global__ void cellid_kernel(const T *x, const T *y, const T *z, int n, Grid g, unsigned int *key, int *idx, int *err) {
+__global__ void cellid_kernel(const T *x, const T *y, const T *z, int n, Grid g, int sub, unsigned int *key, int *idx, int *err) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const double p[3] = {(double) x[i], (double) y[i], (double) z[i]};
   int c[3];
+  unsigned int q[3];            // position inside the cell in quarters (0..3)
 #pragma unroll
   for (int k = 0; k < 3; k++) {
     double u = (p[k] - g.origin[k]) / g.cs[k];
     int ci = (int) floor(u);
     if (g.periodic && !(p[k] >= 0 && p[k] <= g.box[k])) atomicExch(err, 1);   // x == L happens after rounding to float
     c[k] = min(max(ci, 0), g.nc[k] - 1);
+    q[k] = (unsigned int) min(max((int) ((u - c[k]) * 4.0), 0), 3);
   }
-  key[i] = (unsigned int) ((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]);
+  // Sort key: the cell, then (low bits) a Morton code of the position inside the cell.  The counting kernel hands
+  // lane l of a tile the points l, l+32, l+64, ...: with the points of a cell in Morton order every lane gets
+  // primaries from different parts of the cell, which evens out the rate at which the lanes accept pairs.
+  unsigned int m = 0;
+#pragma unroll
+  for (int b = 1; b >= 0; b--) m = (m << 3) | (((q[0] >> b) & 1u) << 2) | (((q[1] >> b) & 1u) << 1) | ((q[2] >> b) & 1u);
+  key[i] = ((unsigned int) ((c[0] * g.nc[1] + c[1]) * g.nc[2] + c[2]) << sub) | (m >> (6 - sub));
   idx[i] = i;
 }
 
@@ -244,11 +252,11 @@ __global__ void gather_kernel(const T *x, const T *y, const T *z, const T *s, co
 }
 
 // cell_start[c] = first sorted index with key >= c (keys sorted ascending), cell_start[ncell] = n
-__global__ void cellstart_kernel(const unsigned int *key, int n, int ncell, int *cell_start) {
+__global__ void cellstart_kernel(const unsigned int *key, int n, int ncell, int sub, int *cell_start) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > n) return;
-  int prev = (i == 0) ? -1 : (int) key[i - 1];
-  int cur = (i == n) ? ncell : (int) key[i];
+  int prev = (i == 0) ? -1 : (int) (key[i - 1] >> sub);
+  int cur = (i == n) ? ncell : (int) (key[i] >> sub);
   for (int c = prev + 1; c <= cur; c++) cell_start[c] = i;
 }
 
@@ -294,10 +302,12 @@ static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool nee
   if (need_w) TRY_(pool_alloc(&S.w, nn * sizeof(T)));
   TRY_(pool_alloc(&S.cell_start, (ncell + 1) * sizeof(int)));
   const int nb = (n + 255) / 256;
+  int bits = 1; while ((1ll << bits) < ncell) bits++;
+  const int sub = getenv("FCFC_GPU_NO_SUBSORT") ? 0 : std::min(6, 31 - bits);   // Morton bits inside the cell
   if (n) {
-    cellid_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z, n, g, key, idx, err);
+    cellid_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z, n, g, sub, key, idx, err);
     g_stats.kernel_launches++;
-    int bits = 1; while ((1ll << bits) < ncell) bits++;
+    bits += sub;
     size_t tb = 0;
     TRY_(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, idx, idx2, n, 0, bits));
     TRY_(pool_alloc(&tmp, tb ? tb : 1));
@@ -307,7 +317,7 @@ static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool nee
                                   idx2, n, S.pos, S.w);
     g_stats.kernel_launches += 2;
   }
-  cellstart_kernel<<<(n + 1 + 255) / 256, 256>>>(key2, n, (int) ncell, S.cell_start);
+  cellstart_kernel<<<(n + 1 + 255) / 256, 256>>>(key2, n, (int) ncell, sub, S.cell_start);
   g_stats.kernel_launches++;
   int herr = 0;
   TRY_(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
