@@ -88,7 +88,8 @@ template <class T> struct CountParams {
   const Vec4<T> *pos2; const T *w2; const int *cell_start2;
   // work items of the primary catalogue: cell id, first point, number of points (<= 32*R)
   const int *item_cell; const int *item_off; const int *item_cnt;
-  int item_begin, item_end;             // this launch (shard) processes items [begin, end)
+  const int *item_order;                // items sorted by decreasing estimated cost (longest first)
+  int nitem, part, nparts;              // this launch (shard) processes order[part], order[part + nparts], ...
   unsigned int *work_counter;           // global queue head (starts at 0)
   // cell grid (cell id = (ix*nc[1] + iy)*nc[2] + iz)
   int nc[3]; int periodic;
@@ -685,9 +686,12 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   // ---- persistent warp loop over work items ----
   while (true) {
     int item = 0;
-    if (lane == 0) item = P.item_begin + (int) atomicAdd(P.work_counter, 1u);
+    if (lane == 0) {
+      const long long w = (long long) P.part + (long long) P.nparts * (long long) atomicAdd(P.work_counter, 1u);
+      item = (w < (long long) P.nitem) ? P.item_order[w] : -1;
+    }
     item = __shfl_sync(0xffffffffu, item, 0);
-    if (item >= P.item_end) break;
+    if (item < 0) break;
     const int cell = P.item_cell[item], t0 = P.item_off[item], cnt = P.item_cnt[item];
     const int iz = cell % ncz, iy = (cell / ncz) % ncy, ix = cell / (ncz * ncy);
     const int nr = (cnt + 31) >> 5;             // primaries per lane actually used by this tile (1..RMAX)

@@ -282,6 +282,35 @@ __global__ void items_kernel(const int *cell_start, const int *tile_off, int nce
   }
 }
 
+// Estimated cost of every work item: its points times the secondary points its stencil sweeps (same range logic
+// as count_kernel).  Items are then processed longest first, and shards take every nparts-th item of that
+// order, which balances clustered catalogues across warps and across GPUs.
+__global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int nitem, const int *cell_start2,
+                                 const int4 *rows, int nrows, int ncx, int ncy, int ncz, int periodic, int isauto,
+                                 float *cost, int *index) {
+  int it = blockIdx.x * blockDim.x + threadIdx.x;
+  if (it >= nitem) return;
+  const int cell = item_cell[it];
+  const int iz = cell % ncz, iy = (cell / ncz) % ncy, ix = cell / (ncz * ncy);
+  long long tot = isauto ? (cell_start2[cell + 1] - cell_start2[cell]) / 2 : 0;
+  for (int r = 0; r < nrows; r++) {
+    const int4 row = rows[r];
+    int jx = ix + row.x, jy = iy + row.y;
+    if (periodic) { jx = (jx % ncx + ncx) % ncx; jy = (jy % ncy + ncy) % ncy; }
+    else if (jx < 0 || jx >= ncx || jy < 0 || jy >= ncy) continue;
+    const int rowbase = (jx * ncy + jy) * ncz;
+    int zlo = iz + row.z, zhi = iz + row.w;
+    if (periodic) {
+      if (zlo < 0) tot += cell_start2[rowbase + min(zhi, -1) + ncz + 1] - cell_start2[rowbase + zlo + ncz];
+      if (zhi >= ncz) tot += cell_start2[rowbase + zhi - ncz + 1] - cell_start2[rowbase + max(zlo, ncz) - ncz];
+    }
+    zlo = max(zlo, 0); zhi = min(zhi, ncz - 1);
+    if (zlo <= zhi) tot += cell_start2[rowbase + zhi + 1] - cell_start2[rowbase + zlo];
+  }
+  cost[it] = (float) tot * (float) item_cnt[it];
+  index[it] = it;
+}
+
 // ------------------------------------------------------------------------------------------
 template <class T>
 static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool need_w, float *ms_out) {
@@ -411,7 +440,9 @@ static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[
                         double n1, double n2, int tile, bool half) {
   Grid best; double best_cost = 1e300;
   const double rxy = std::sqrt(R.r2_xy), rz = R.r_z;
-  for (int k = 1; k <= 12; k++) {
+  int kmin = 1, kmax = 12;
+  if (const char *ek = getenv("FCFC_GPU_K")) kmin = kmax = std::max(1, atoi(ek));     // experiment hook: force reach/cell
+  for (int k = kmin; k <= kmax; k++) {
     Grid g; g.periodic = b->periodic;
     bool ok = true;
     for (int d = 0; d < 3; d++) {
@@ -535,8 +566,26 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   P.pos1 = S1.pos; P.w1 = S1.w; P.pos2 = S2.pos; P.w2 = S2.w; P.cell_start2 = S2.cell_start;
   P.item_cell = S1.item_cell; P.item_off = S1.item_off; P.item_cnt = S1.item_cnt;
   // shard: contiguous item ranges (cells are visited in memory order; cost balancing by item count)
-  const long long ni = S1.nitem;
-  P.item_begin = (int) (ni * part / nparts); P.item_end = (int) (ni * (part + 1) / nparts);
+  // longest-first order of the work items (cost depends on the secondary catalogue and the stencil)
+  int *d_order = nullptr;
+  {
+    const int ni = S1.nitem;
+    float *cost = nullptr, *cost2 = nullptr; int *idx = nullptr; void *tmp = nullptr;
+    auto fail = [&](const char *what) { pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp); pool_free(d_order); pool_free(dbuf); set_err("%s", what); return FCFC_GPU_ERR_TREE; };
+    if (pool_alloc(&cost, (size_t) ni * 4) || pool_alloc(&cost2, (size_t) ni * 4) || pool_alloc(&idx, (size_t) ni * 4) ||
+        pool_alloc(&d_order, (size_t) ni * 4)) return fail("out of device memory for the work-item order");
+    if (ni) {
+      item_cost_kernel<<<(ni + 255) / 256, 256>>>(S1.item_cell, S1.item_cnt, ni, S2.cell_start, reinterpret_cast<const int4 *>(dbuf + o_rows),
+                                                  (int) rows.size(), g.nc[0], g.nc[1], g.nc[2], b->periodic, isauto, cost, idx);
+      g_stats.kernel_launches++;
+      size_t tb = 0;
+      if (cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, cost, cost2, idx, d_order, ni) != cudaSuccess) return fail("cub sort failed");
+      if (pool_alloc(&tmp, tb ? tb : 1)) return fail("out of device memory for the work-item order");
+      if (cub::DeviceRadixSort::SortPairsDescending(tmp, tb, cost, cost2, idx, d_order, ni) != cudaSuccess) return fail("cub sort failed");
+    }
+    pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp);
+  }
+  P.item_order = d_order; P.nitem = S1.nitem; P.part = part; P.nparts = nparts;
   P.work_counter = reinterpret_cast<unsigned int *>(dbuf + o_cnt);
   for (int d = 0; d < 3; d++) { P.nc[d] = g.nc[d]; P.bsize[d] = (T) b->bsize[d]; }
   P.periodic = b->periodic;
@@ -626,20 +675,21 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
     }
     if (depth) break;
   }
-  if (!depth) { pool_free(dbuf); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  if (!depth) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   P.qdepth = depth;
   cudaEventRecord(ev1);
-  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (P.item_end - P.item_begin + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
+  const int my_items = (S1.nitem - part + nparts - 1) / nparts;
+  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(ev2);
-  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); pool_free(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); pool_free(dbuf); pool_free(d_order); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   // ---- results ----
   cudaError_t ce = cudaMemcpy(withwt ? (void *) cnt_d : (void *) cnt_i, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToHost);
-  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); pool_free(dbuf); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); pool_free(dbuf); pool_free(d_order); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   if (dev_hist) cudaMemcpy(dev_hist, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToDevice);
   unsigned long long ev = 0;
   cudaMemcpy(&ev, dbuf + o_cnt + 8, 8, cudaMemcpyDeviceToHost);
@@ -650,9 +700,9 @@ static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu
   if (!withwt && cnt_i) { unsigned long long t = 0; for (size_t i = 0; i < ntot; i++) t += (unsigned long long) cnt_i[i]; g_stats.pairs_in = t; }
   g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];
-  g_stats.nitem = P.item_end - P.item_begin;
+  g_stats.nitem = my_items;
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
-  pool_free(dbuf);
+  pool_free(dbuf); pool_free(d_order);
   return 0;
 }
 

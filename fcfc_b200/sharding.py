@@ -7,10 +7,18 @@ from __future__ import annotations
 
 
 def item_range(nitem: int, part: int, nparts: int) -> tuple[int, int]:
-    """[begin, end) of the work items of shard `part` (same arithmetic as engine.cu)."""
+    """[begin, end) of a contiguous split of `nitem` units into `nparts` (used to shard host-side arrays)."""
     if not (0 <= part < nparts):
         raise ValueError("invalid shard")
     return nitem * part // nparts, nitem * (part + 1) // nparts
+
+
+def shard_items(nitem: int, part: int, nparts: int) -> range:
+    """Work items of shard `part` as the engine assigns them (engine.cu / count_kernel.cuh): the items are sorted
+    by decreasing estimated cost and shard `part` takes positions part, part + nparts, ... of that order."""
+    if not (0 <= part < nparts):
+        raise ValueError("invalid shard")
+    return range(part, nitem, nparts)
 
 
 def allreduce_histogram(hist, group=None):

@@ -11,7 +11,7 @@ import torch.distributed as dist
 import torch.multiprocessing as mp
 
 from cases import box_catalog
-from fcfc_b200.sharding import allreduce_histogram, item_range
+from fcfc_b200.sharding import allreduce_histogram, item_range, shard_items
 from oracle import oracle
 
 
@@ -29,6 +29,10 @@ def test_item_ranges_partition_exactly():
                 assert seen[0][0] == 0 and seen[-1][1] == nitem and all(seen[i][1] == seen[i + 1][0] for i in range(nparts - 1))
     with pytest.raises(ValueError):
         item_range(10, 2, 2)
+    for nitem in (0, 1, 7, 100):
+        for nparts in (1, 2, 3, 8):
+            seen = sorted(i for p in range(nparts) for i in shard_items(nitem, p, nparts))
+            assert seen == list(range(nitem))
 
 
 def _worker(rank, world, port, out):
