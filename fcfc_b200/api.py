@@ -255,9 +255,14 @@ def count_pairs(cat1: Catalog, cat2: Catalog | None, bins: Bins, *, withwt: bool
     isauto = cat2 is None or cat2 is cat1
     c2 = cat1 if isauto else cat2
     out = np.zeros(bins.ntot, dtype=np.float64 if withwt else np.int64)
-    rc = L.fcfc_gpu_count_partial(cat1._h, c2._h, bins.c, int(isauto), int(withwt), part, nparts,
-                                  None if withwt else out.ctypes.data, out.ctypes.data if withwt else None,
-                                  dev_hist_ptr)
+    if nparts == 1 and dev_hist_ptr is None:
+        # the whole count, over every device the process is bound to (one all-reduce of the histograms)
+        rc = L.fcfc_gpu_count(cat1._h, c2._h, bins.c, int(isauto), int(withwt),
+                              None if withwt else out.ctypes.data, out.ctypes.data if withwt else None)
+    else:
+        rc = L.fcfc_gpu_count_partial(cat1._h, c2._h, bins.c, int(isauto), int(withwt), part, nparts,
+                                      None if withwt else out.ctypes.data, out.ctypes.data if withwt else None,
+                                      dev_hist_ptr)
     if rc != 0:
         raise FcfcGpuError(last_error(), rc)
     return out

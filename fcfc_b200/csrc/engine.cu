@@ -17,7 +17,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <dlfcn.h>
+#include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace fcfc {
@@ -60,10 +63,12 @@ static int ensure_init() {
 // blocks are kept and handed out again (first fit within 2x).  Everything is returned by fcfc_gpu_finalize.
 struct PoolBlock { void *p; size_t bytes; int dev; };
 static std::vector<PoolBlock> g_pool_free, g_pool_used;
+static std::mutex g_pool_mutex;    // fcfc_gpu_count drives several devices from worker threads
 static size_t g_pool_cached = 0;
 static const size_t kPoolMaxCached = (size_t) 48 << 30;
 
 static cudaError_t pool_alloc(void **out, size_t bytes) {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
   int dev = 0; cudaGetDevice(&dev);
   bytes = (bytes + 511) & ~(size_t) 511;
   if (bytes == 0) bytes = 512;
@@ -94,6 +99,7 @@ static cudaError_t pool_alloc(void **out, size_t bytes) {
 }
 static void pool_free(void *p) {
   if (!p) return;
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (size_t i = 0; i < g_pool_used.size(); i++)
     if (g_pool_used[i].p == p) {
       PoolBlock b = g_pool_used[i];
@@ -105,6 +111,7 @@ static void pool_free(void *p) {
   cudaFree(p);
 }
 static void pool_release_all() {
+  std::lock_guard<std::mutex> lock(g_pool_mutex);
   for (auto &b : g_pool_free) cudaFree(b.p);
   g_pool_free.clear(); g_pool_cached = 0;
 }
@@ -143,7 +150,8 @@ template <class T> struct Sorted {
 
 }  // namespace fcfc
 
-struct fcfc_gpu_catalog {
+// One device's copy of a catalogue.
+struct DevCat {
   int is_float = 0;
   size_t n = 0;
   int device = 0;
@@ -156,11 +164,20 @@ struct fcfc_gpu_catalog {
   fcfc::Sorted<double> sd;
 };
 
+// The public handle: one replica per device in use (the secondary catalogue must be resident everywhere).
+struct fcfc_gpu_catalog {
+  int is_float = 0;
+  size_t n = 0;
+  double wsum = 0;
+  bool has_w = false;
+  std::vector<DevCat *> dev;
+};
+
 namespace fcfc {
 
-template <class T> static Sorted<T> &sorted_of(fcfc_gpu_catalog *c);
-template <> Sorted<float> &sorted_of<float>(fcfc_gpu_catalog *c) { return c->sf; }
-template <> Sorted<double> &sorted_of<double>(fcfc_gpu_catalog *c) { return c->sd; }
+template <class T> static Sorted<T> &sorted_of(DevCat *c);
+template <> Sorted<float> &sorted_of<float>(DevCat *c) { return c->sf; }
+template <> Sorted<double> &sorted_of<double>(DevCat *c) { return c->sd; }
 
 // ------------------------------------------------------------------------------------------
 // catalogue kernels
@@ -313,7 +330,7 @@ __global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int 
 
 // ------------------------------------------------------------------------------------------
 template <class T>
-static int build_sorted(fcfc_gpu_catalog *cat, const Grid &g, int tile, bool need_w, float *ms_out) {
+static int build_sorted(DevCat *cat, const Grid &g, int tile, bool need_w, float *ms_out) {
   Sorted<T> &S = sorted_of<T>(cat);
   if (S.valid && S.grid == g && S.tile == tile && (!need_w || S.w)) return 0;
   S.release();
@@ -479,7 +496,7 @@ static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[
 
 // ------------------------------------------------------------------------------------------
 template <class T>
-static int count_impl(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
+static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
                       int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
   const bool is_float = sizeof(T) == 4;
   const int bintype = b->bintype;
@@ -715,8 +732,11 @@ using namespace fcfc;
 extern "C" int fcfc_gpu_abi_version(void) { return FCFC_GPU_ABI_VERSION; }
 extern "C" const char *fcfc_gpu_last_error(void) { return g_err.c_str(); }
 
+static void nccl_reset();
+
 extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
   g_verbose = verbose;
+  nccl_reset();          // communicators belong to a device set
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
   if (e != cudaSuccess || count == 0) {
@@ -742,10 +762,14 @@ extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
   return (int) g_ctx.devices.size();
 }
 
-extern "C" void fcfc_gpu_finalize(void) { pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear(); }
+extern "C" void fcfc_gpu_finalize(void) {
+  for (int d : g_ctx.devices) { cudaSetDevice(d); cudaDeviceSynchronize(); }
+  nccl_reset();
+  pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear();
+}
 
 template <class T>
-static int catalog_upload(fcfc_gpu_catalog *c, const void *x, const void *y, const void *z, const void *s, const void *w,
+static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z, const void *s, const void *w,
                           double rescale, int sumsq) {
   const size_t n = c->n, bytes = (n ? n : 1) * sizeof(T);
   CUDA_TRY(pool_alloc(&c->x, bytes), FCFC_GPU_ERR_MEMORY);
@@ -794,40 +818,157 @@ extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *
   if (n && (!x || !y || !z)) { set_err("NULL coordinate array"); return nullptr; }
   if (n >= (1ull << 31) - 64) { set_err("catalogue too large for 32-bit point indices"); return nullptr; }
   fcfc_gpu_catalog *c = new fcfc_gpu_catalog();
-  c->is_float = is_float; c->n = n; c->device = g_ctx.devices[0];
-  cudaSetDevice(c->device);
-  int e = is_float ? catalog_upload<float>(c, x, y, z, x2sum, w, rescale, sumsq_arith)
-                   : catalog_upload<double>(c, x, y, z, x2sum, w, rescale, sumsq_arith);
-  if (e) { fcfc_gpu_catalog_destroy(c); return nullptr; }
+  c->is_float = is_float; c->n = n; c->has_w = w != nullptr;
+  for (int d : g_ctx.devices) {         // one replica per device (host -> each device)
+    DevCat *dc = new DevCat();
+    dc->is_float = is_float; dc->n = n; dc->device = d;
+    c->dev.push_back(dc);
+    cudaSetDevice(d);
+    int e = is_float ? catalog_upload<float>(dc, x, y, z, x2sum, w, rescale, sumsq_arith)
+                     : catalog_upload<double>(dc, x, y, z, x2sum, w, rescale, sumsq_arith);
+    if (e) { fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
+  }
+  c->wsum = c->dev[0]->wsum;
+  cudaSetDevice(g_ctx.devices[0]);
   return c;
 }
 
 extern "C" void fcfc_gpu_catalog_destroy(fcfc_gpu_catalog *c) {
   if (!c) return;
-  pool_free(c->x); pool_free(c->y); pool_free(c->z); pool_free(c->s); pool_free(c->w);
-  c->sf.release(); c->sd.release();
+  for (DevCat *dc : c->dev) {
+    cudaSetDevice(dc->device);
+    pool_free(dc->x); pool_free(dc->y); pool_free(dc->z); pool_free(dc->s); pool_free(dc->w);
+    dc->sf.release(); dc->sd.release();
+    delete dc;
+  }
+  if (g_ctx.ready && !g_ctx.devices.empty()) cudaSetDevice(g_ctx.devices[0]);
   delete c;
 }
 extern "C" size_t fcfc_gpu_catalog_size(const fcfc_gpu_catalog *c) { return c ? c->n : 0; }
 extern "C" double fcfc_gpu_catalog_wsum(const fcfc_gpu_catalog *c) { return c ? c->wsum : 0; }
 
-extern "C" int fcfc_gpu_count_partial(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto,
-                                      int withwt, int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
+static int check_count_args(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
+                            const int64_t *cnt_i, const double *cnt_d) {
   if (ensure_init()) return FCFC_GPU_ERR_CUDA;
   if (!c1 || !c2 || !b) { set_err("NULL argument"); return FCFC_GPU_ERR_ARG; }
   if ((withwt && !cnt_d) || (!withwt && !cnt_i)) { set_err("missing output array"); return FCFC_GPU_ERR_ARG; }
   if (c1->is_float != c2->is_float || c1->is_float != (b->is_float != 0)) { set_err("precision mismatch between catalogues and bins"); return FCFC_GPU_ERR_ARG; }
-  if (nparts < 1 || part < 0 || part >= nparts) { set_err("invalid shard %d/%d", part, nparts); return FCFC_GPU_ERR_ARG; }
   if (isauto && c1 != c2) { set_err("auto count needs cat1 == cat2"); return FCFC_GPU_ERR_ARG; }
-  if (withwt && (!c1->has_w && !c2->has_w)) { /* both unit weights: allowed, like the reference's w = 1 fill */ }
-  cudaSetDevice(c1->device);
-  return b->is_float ? count_impl<float>(c1, c2, b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist)
-                     : count_impl<double>(c1, c2, b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist);
+  if (c1->dev.empty() || c1->dev.size() != c2->dev.size()) { set_err("catalogues are resident on different device sets"); return FCFC_GPU_ERR_ARG; }
+  return 0;
 }
 
+extern "C" int fcfc_gpu_count_partial(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto,
+                                      int withwt, int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
+  int e = check_count_args(c1, c2, b, isauto, withwt, cnt_i, cnt_d);
+  if (e) return e;
+  if (nparts < 1 || part < 0 || part >= nparts) { set_err("invalid shard %d/%d", part, nparts); return FCFC_GPU_ERR_ARG; }
+  cudaSetDevice(c1->dev[0]->device);
+  return b->is_float ? count_impl<float>(c1->dev[0], c2->dev[0], b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist)
+                     : count_impl<double>(c1->dev[0], c2->dev[0], b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist);
+}
+
+// ---- NCCL, bound at run time (only needed when one process drives several devices) -------------------
+namespace {
+struct Nccl {
+  void *lib = nullptr;
+  int (*CommInitAll)(void **, int, const int *) = nullptr;
+  int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
+  int (*GroupStart)() = nullptr;
+  int (*GroupEnd)() = nullptr;
+  int (*CommDestroy)(void *) = nullptr;
+  const char *(*GetErrorString)(int) = nullptr;
+  std::vector<void *> comms;
+  bool ready = false, tried = false;
+};
+Nccl g_nccl;
+bool nccl_setup() {
+  if (g_nccl.tried) return g_nccl.ready;
+  g_nccl.tried = true;
+  for (const char *name : {"libnccl.so.2", "libnccl.so"}) { g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
+  if (!g_nccl.lib) return false;
+#define FCFC_SYM(f, n) g_nccl.f = reinterpret_cast<decltype(g_nccl.f)>(dlsym(g_nccl.lib, n)); if (!g_nccl.f) return false;
+  FCFC_SYM(CommInitAll, "ncclCommInitAll") FCFC_SYM(AllReduce, "ncclAllReduce") FCFC_SYM(GroupStart, "ncclGroupStart")
+  FCFC_SYM(GroupEnd, "ncclGroupEnd") FCFC_SYM(CommDestroy, "ncclCommDestroy") FCFC_SYM(GetErrorString, "ncclGetErrorString")
+#undef FCFC_SYM
+  g_nccl.comms.assign(g_ctx.devices.size(), nullptr);
+  if (g_nccl.CommInitAll(g_nccl.comms.data(), (int) g_ctx.devices.size(), g_ctx.devices.data()) != 0) return false;
+  g_nccl.ready = true;
+  return true;
+}
+}  // namespace
+
+static void nccl_reset() {
+  if (g_nccl.ready) for (void *c : g_nccl.comms) if (c) g_nccl.CommDestroy(c);
+  g_nccl.comms.clear(); g_nccl.ready = false; g_nccl.tried = false;
+}
+
+// count_pairs() over every device in use: device d counts shard d of the primary catalogue's work items
+// against its replica of the secondary catalogue (one host thread per device), then the per-device
+// histograms are summed with one ncclAllReduce (int64 / float64, ntot elements) and read back once.
 extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
                               int64_t *cnt_i, double *cnt_d) {
-  return fcfc_gpu_count_partial(c1, c2, b, isauto, withwt, 0, 1, cnt_i, cnt_d, nullptr);
+  int e = check_count_args(c1, c2, b, isauto, withwt, cnt_i, cnt_d);
+  if (e) return e;
+  const int ndev = (int) c1->dev.size();
+  if (ndev == 1) return fcfc_gpu_count_partial(c1, c2, b, isauto, withwt, 0, 1, cnt_i, cnt_d, nullptr);
+  const int bt = b->bintype;
+  const size_t ntot = (size_t) b->ns * (bt == FCFC_GPU_BIN_ISO ? 1 : (bt == FCFC_GPU_BIN_SMU ? b->nmu : b->np));
+  std::vector<void *> dhist(ndev, nullptr);
+  std::vector<std::vector<unsigned char>> part(ndev, std::vector<unsigned char>(ntot * 8));
+  std::vector<int> rc(ndev, 0);
+  std::vector<std::string> errs(ndev);
+  std::vector<fcfc_gpu_stats> st(ndev);
+  for (int d = 0; d < ndev; d++) {
+    cudaSetDevice(c1->dev[d]->device);
+    if (pool_alloc(&dhist[d], ntot * 8) != cudaSuccess) { set_err("out of device memory"); return FCFC_GPU_ERR_MEMORY; }
+  }
+  std::vector<std::thread> th;
+  for (int d = 0; d < ndev; d++)
+    th.emplace_back([&, d]() {
+      cudaSetDevice(c1->dev[d]->device);
+      int64_t *pi = withwt ? nullptr : reinterpret_cast<int64_t *>(part[d].data());
+      double *pd = withwt ? reinterpret_cast<double *>(part[d].data()) : nullptr;
+      rc[d] = b->is_float ? count_impl<float>(c1->dev[d], c2->dev[d], b, isauto, withwt, d, ndev, pi, pd, dhist[d])
+                          : count_impl<double>(c1->dev[d], c2->dev[d], b, isauto, withwt, d, ndev, pi, pd, dhist[d]);
+      if (rc[d]) errs[d] = g_err;
+      st[d] = g_stats;
+    });
+  for (auto &t : th) t.join();
+  int bad = 0;
+  for (int d = 0; d < ndev; d++) if (rc[d]) { bad = rc[d]; g_err = errs[d]; }
+  if (!bad) {
+    if (nccl_setup()) {
+      int ne = g_nccl.GroupStart();
+      for (int d = 0; d < ndev && !ne; d++) {
+        cudaSetDevice(c1->dev[d]->device);
+        ne = g_nccl.AllReduce(dhist[d], dhist[d], ntot, withwt ? 8 /* ncclFloat64 */ : 4 /* ncclInt64 */, 0 /* ncclSum */, g_nccl.comms[d], 0);
+      }
+      if (!ne) ne = g_nccl.GroupEnd(); else g_nccl.GroupEnd();
+      cudaSetDevice(c1->dev[0]->device);
+      if (ne || cudaMemcpy(withwt ? (void *) cnt_d : (void *) cnt_i, dhist[0], ntot * 8, cudaMemcpyDeviceToHost) != cudaSuccess) {
+        set_err("NCCL all-reduce of the histograms failed: %s", ne ? g_nccl.GetErrorString(ne) : "copy back"); bad = FCFC_GPU_ERR_CUDA;
+      }
+    } else {
+      // no NCCL library on this host: add the ntot-element partial histograms that are already on the host
+      if (g_verbose) fprintf(stderr, "[fcfc_gpu] libnccl not found: summing the per-device histograms on the host\n");
+      for (size_t k = 0; k < ntot; k++) {
+        if (withwt) { double v = 0; for (int d = 0; d < ndev; d++) v += reinterpret_cast<double *>(part[d].data())[k]; cnt_d[k] = v; }
+        else { int64_t v = 0; for (int d = 0; d < ndev; d++) v += reinterpret_cast<int64_t *>(part[d].data())[k]; cnt_i[k] = v; }
+      }
+    }
+  }
+  for (int d = 0; d < ndev; d++) { cudaSetDevice(c1->dev[d]->device); pool_free(dhist[d]); }
+  cudaSetDevice(c1->dev[0]->device);
+  // statistics: sums over the devices, times are the slowest device
+  g_stats = st[0];
+  for (int d = 1; d < ndev; d++) {
+    g_stats.pair_evals += st[d].pair_evals; g_stats.kernel_launches += st[d].kernel_launches; g_stats.nitem += st[d].nitem;
+    g_stats.ms_sort = std::max(g_stats.ms_sort, st[d].ms_sort); g_stats.ms_count = std::max(g_stats.ms_count, st[d].ms_count);
+    g_stats.ms_total = std::max(g_stats.ms_total, st[d].ms_total);
+  }
+  if (!bad && !withwt) { unsigned long long t = 0; for (size_t k = 0; k < ntot; k++) t += (unsigned long long) cnt_i[k]; g_stats.pairs_in = t; }
+  return bad;
 }
 
 extern "C" int fcfc_gpu_get_stats(fcfc_gpu_stats *out) {
