@@ -90,6 +90,7 @@ template <class T> struct CountParams {
   const int *item_cell; const int *item_off; const int *item_cnt;
   const int *item_order;                // items sorted by decreasing estimated cost (longest first)
   int nitem, part, nparts;              // this launch (shard) processes order[part], order[part + nparts], ...
+  int nsplit;                           // every tile's sweep list is cut into nsplit work items (small problems)
   unsigned int *work_counter;           // global queue head (starts at 0)
   // cell grid (cell id = (ix*nc[1] + iy)*nc[2] + iz)
   int nc[3]; int periodic;
@@ -97,7 +98,7 @@ template <class T> struct CountParams {
   // neighbour stencil: rows (dx, dy, dz_lo, dz_hi)
   const int4 *rows; int nrows;
   // binning
-  T s2min, s2max, pmin, pmax, premax, nmu2f;
+  T s2min, s2max, pmin, pmax, premax, pmax_pre, nmu2f;
   int ns, np, nmu2, ntot, soff, poff;
   int tab_hybrid, swidth, pwidth, with_mu_one, smin0, pmin0;
   int mu_is_sqrt, stab_is_sqrt, ptab_is_ident;     // tables that equal floor(sqrt(i)) / i are computed, not looked up
@@ -248,6 +249,13 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
     d2 = A::sub(s, t);
     aux = t;
     ok = d2 < ((BIN == BIN_SPI) ? P.premax : P.s2max);
+    if (BIN == BIN_SPI) {
+      // cheap necessary condition for pi^2 = d*d / (s + t) < p2max, without the division (the exact test is
+      // repeated in finish_pair): d*d < (s + t) * p2max * (1 + 8 eps).  Cuts the queue traffic of survey
+      // (s_perp, pi) counts, whose accepted region is a thin cylinder inside the searched sphere.
+      const T d = A::sub(as, b.s);
+      ok = ok && (A::mul(d, d) < A::mul(A::add(s, t), P.pmax_pre));
+    }
   }
   if (GENERIC && BIN != BIN_SPI) ok = ok && (P.smin0 || d2 >= P.s2min);
   if (GENERIC && BIN == BIN_SPI && BOX) ok = ok && (P.smin0 || d2 >= P.s2min);
@@ -692,7 +700,8 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     }
     item = __shfl_sync(0xffffffffu, item, 0);
     if (item < 0) break;
-    const int cell = P.item_cell[item], t0 = P.item_off[item], cnt = P.item_cnt[item];
+    const int tile_id = item / P.nsplit, split = item - tile_id * P.nsplit;
+    const int cell = P.item_cell[tile_id], t0 = P.item_off[tile_id], cnt = P.item_cnt[tile_id];
     const int iz = cell % ncz, iy = (cell / ncz) % ncy, ix = cell / (ncz * ncy);
     const int nr = (cnt + 31) >> 5;             // primaries per lane actually used by this tile (1..RMAX)
 
@@ -778,8 +787,10 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     // q = 3*row + image enumerates, for every stencil row, the three periodic images of its z run
     // (below the box: the primaries get +L in z; inside; above the box: the secondaries get +L).
     // A single call site keeps the unrolled pair loops in the instruction cache.
-    const int nq = (P.periodic ? 3 : 1) * P.nrows;
-    for (int q = P.isauto ? -1 : 0; q < nq; q++) {
+    const int nq = (P.periodic ? 3 : 1) * P.nrows, qfirst = P.isauto ? -1 : 0;
+    const int qlo = qfirst + (int) ((long long) (nq - qfirst) * split / P.nsplit);
+    const int qhi = qfirst + (int) ((long long) (nq - qfirst) * (split + 1) / P.nsplit);
+    for (int q = qlo; q < qhi; q++) {
       int b, e;
       T sax = 0, say = 0, saz = 0, sbx = 0, sby = 0, sbz = 0;
       if (q < 0) { b = t0; e = P.cell_start2[cell + 1]; }

@@ -302,29 +302,38 @@ __global__ void items_kernel(const int *cell_start, const int *tile_off, int nce
 // Estimated cost of every work item: its points times the secondary points its stencil sweeps (same range logic
 // as count_kernel).  Items are then processed longest first, and shards take every nparts-th item of that
 // order, which balances clustered catalogues across warps and across GPUs.
-__global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int nitem, const int *cell_start2,
+__global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int ntile, int nsplit, const int *cell_start2,
                                  const int4 *rows, int nrows, int ncx, int ncy, int ncz, int periodic, int isauto,
                                  float *cost, int *index) {
   int it = blockIdx.x * blockDim.x + threadIdx.x;
-  if (it >= nitem) return;
-  const int cell = item_cell[it];
+  if (it >= ntile * nsplit) return;
+  const int tile = it / nsplit, split = it - tile * nsplit;
+  const int cell = item_cell[tile];
   const int iz = cell % ncz, iy = (cell / ncz) % ncy, ix = cell / (ncz * ncy);
-  long long tot = isauto ? (cell_start2[cell + 1] - cell_start2[cell]) / 2 : 0;
-  for (int r = 0; r < nrows; r++) {
-    const int4 row = rows[r];
+  const int nq = (periodic ? 3 : 1) * nrows, qfirst = isauto ? -1 : 0;
+  const int qlo = qfirst + (int) ((long long) (nq - qfirst) * split / nsplit);
+  const int qhi = qfirst + (int) ((long long) (nq - qfirst) * (split + 1) / nsplit);
+  long long tot = 0;
+  for (int q = qlo; q < qhi; q++) {
+    if (q < 0) { tot += (cell_start2[cell + 1] - cell_start2[cell]) / 2; continue; }
+    const int ri = periodic ? q / 3 : q, img = periodic ? q - 3 * ri : 1;
+    const int4 row = rows[ri];
     int jx = ix + row.x, jy = iy + row.y;
-    if (periodic) { jx = (jx % ncx + ncx) % ncx; jy = (jy % ncy + ncy) % ncy; }
-    else if (jx < 0 || jx >= ncx || jy < 0 || jy >= ncy) continue;
-    const int rowbase = (jx * ncy + jy) * ncz;
     int zlo = iz + row.z, zhi = iz + row.w;
     if (periodic) {
-      if (zlo < 0) tot += cell_start2[rowbase + min(zhi, -1) + ncz + 1] - cell_start2[rowbase + zlo + ncz];
-      if (zhi >= ncz) tot += cell_start2[rowbase + zhi - ncz + 1] - cell_start2[rowbase + max(zlo, ncz) - ncz];
+      jx = (jx % ncx + ncx) % ncx; jy = (jy % ncy + ncy) % ncy;
+      if (img == 0) { zhi = min(zhi, -1) + ncz; zlo += ncz; }
+      else if (img == 1) { zlo = max(zlo, 0); zhi = min(zhi, ncz - 1); }
+      else { zlo = max(zlo, ncz) - ncz; zhi -= ncz; }
+    } else {
+      if (jx < 0 || jx >= ncx || jy < 0 || jy >= ncy) continue;
+      zlo = max(zlo, 0); zhi = min(zhi, ncz - 1);
     }
-    zlo = max(zlo, 0); zhi = min(zhi, ncz - 1);
-    if (zlo <= zhi) tot += cell_start2[rowbase + zhi + 1] - cell_start2[rowbase + zlo];
+    if (zlo > zhi) continue;
+    const int rowbase = (jx * ncy + jy) * ncz;
+    tot += cell_start2[rowbase + zhi + 1] - cell_start2[rowbase + zlo];
   }
-  cost[it] = (float) tot * (float) item_cnt[it];
+  cost[it] = (float) tot * (float) item_cnt[tile] + 1.0f;
   index[it] = it;
 }
 
@@ -584,15 +593,20 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   P.item_cell = S1.item_cell; P.item_off = S1.item_off; P.item_cnt = S1.item_cnt;
   // shard: contiguous item ranges (cells are visited in memory order; cost balancing by item count)
   // longest-first order of the work items (cost depends on the secondary catalogue and the stencil)
-  int *d_order = nullptr;
+  int *d_order = nullptr, nsplit = 1;
   {
-    const int ni = S1.nitem;
+    // small problems: cut every tile's sweep list so that each warp of the grid still gets several work items
+    const long long warps_total = (long long) g_ctx.sm_count * BlockShape<T>::kWarps;
+    const int nq_all = (int) rows.size() * (b->periodic ? 3 : 1) + (isauto ? 1 : 0);
+    nsplit = (int) std::min<long long>(std::max<long long>(1, (8 * warps_total * nparts + S1.nitem - 1) / std::max(S1.nitem, 1)), std::max(nq_all, 1));
+    if (const char *es = getenv("FCFC_GPU_NSPLIT")) nsplit = std::max(1, std::min(atoi(es), std::max(nq_all, 1)));
+    const int ni = S1.nitem * nsplit;
     float *cost = nullptr, *cost2 = nullptr; int *idx = nullptr; void *tmp = nullptr;
     auto fail = [&](const char *what) { pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp); pool_free(d_order); pool_free(dbuf); set_err("%s", what); return FCFC_GPU_ERR_TREE; };
     if (pool_alloc(&cost, (size_t) ni * 4) || pool_alloc(&cost2, (size_t) ni * 4) || pool_alloc(&idx, (size_t) ni * 4) ||
         pool_alloc(&d_order, (size_t) ni * 4)) return fail("out of device memory for the work-item order");
     if (ni) {
-      item_cost_kernel<<<(ni + 255) / 256, 256>>>(S1.item_cell, S1.item_cnt, ni, S2.cell_start, reinterpret_cast<const int4 *>(dbuf + o_rows),
+      item_cost_kernel<<<(ni + 255) / 256, 256>>>(S1.item_cell, S1.item_cnt, S1.nitem, nsplit, S2.cell_start, reinterpret_cast<const int4 *>(dbuf + o_rows),
                                                   (int) rows.size(), g.nc[0], g.nc[1], g.nc[2], b->periodic, isauto, cost, idx);
       g_stats.kernel_launches++;
       size_t tb = 0;
@@ -602,7 +616,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     }
     pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp);
   }
-  P.item_order = d_order; P.nitem = S1.nitem; P.part = part; P.nparts = nparts;
+  P.item_order = d_order; P.nitem = S1.nitem * nsplit; P.nsplit = nsplit; P.part = part; P.nparts = nparts;
   P.work_counter = reinterpret_cast<unsigned int *>(dbuf + o_cnt);
   for (int d = 0; d < 3; d++) { P.nc[d] = g.nc[d]; P.bsize[d] = (T) b->bsize[d]; }
   P.periodic = b->periodic;
@@ -612,6 +626,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     // survey (s_perp, pi): cheap pre-test s^2 < s2max + p2max before the division (see eval_pair)
     double pm = (s2max + pmax) * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
     P.premax = (T) pm; if ((double) P.premax < pm) P.premax = std::nextafter(P.premax, (T) INFINITY);
+    const double pp = pmax * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
+    P.pmax_pre = (T) pp; if ((double) P.pmax_pre < pp) P.pmax_pre = std::nextafter(P.pmax_pre, (T) INFINITY);
   }
   P.nmu2 = nmu * nmu; P.nmu2f = (T) (nmu * nmu);
   P.ns = ns; P.np = np; P.ntot = (int) ntot;
@@ -698,7 +714,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   P.qdepth = depth;
   cudaEventRecord(ev1);
-  const int my_items = (S1.nitem - part + nparts - 1) / nparts;
+  const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
@@ -863,6 +879,7 @@ extern "C" int fcfc_gpu_count_partial(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2
   int e = check_count_args(c1, c2, b, isauto, withwt, cnt_i, cnt_d);
   if (e) return e;
   if (nparts < 1 || part < 0 || part >= nparts) { set_err("invalid shard %d/%d", part, nparts); return FCFC_GPU_ERR_ARG; }
+  if (!isauto && c2->n > c1->n) std::swap(c1, c2);      // cross counts are symmetric: the larger catalogue supplies the tiles
   cudaSetDevice(c1->dev[0]->device);
   return b->is_float ? count_impl<float>(c1->dev[0], c2->dev[0], b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist)
                      : count_impl<double>(c1->dev[0], c2->dev[0], b, isauto, withwt, part, nparts, cnt_i, cnt_d, dev_hist);
@@ -912,6 +929,7 @@ extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const 
   if (e) return e;
   const int ndev = (int) c1->dev.size();
   if (ndev == 1) return fcfc_gpu_count_partial(c1, c2, b, isauto, withwt, 0, 1, cnt_i, cnt_d, nullptr);
+  if (!isauto && c2->n > c1->n) std::swap(c1, c2);      // cross counts are symmetric: the larger catalogue supplies the tiles
   const int bt = b->bintype;
   const size_t ntot = (size_t) b->ns * (bt == FCFC_GPU_BIN_ISO ? 1 : (bt == FCFC_GPU_BIN_SMU ? b->nmu : b->np));
   std::vector<void *> dhist(ndev, nullptr);
