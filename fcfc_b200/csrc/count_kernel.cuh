@@ -133,7 +133,8 @@ __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, in
   SmemPlan p;
   int o = 0;
   auto al = [](int v) { return (v + 15) & ~15; };
-  p.off_hist = o; o += smem_hist ? al(ntot * (WT ? 8 * hist_copies : 4)) : 0;
+  // unweighted: bins 0 .. ntot + ns (the fast drain may land a flagged pair one row / column outside) + 32 per-lane dump slots
+  p.off_hist = o; o += smem_hist ? al(WT ? ntot * 8 * hist_copies : (ntot + ns + 1 + 32) * 4) : 0;
   p.off_stab = o; o += tabs_global ? 0 : al(nstab_bytes);
   p.off_ptab = o; o += tabs_global ? 0 : al(nptab_bytes);
   p.off_mutab = o; o += tabs_global ? 0 : al(nmutab_bytes);
@@ -147,6 +148,7 @@ __host__ __device__ inline SmemPlan make_smem_plan(int ntot, int nstab_bytes, in
   p.off_queue = o;
   p.queue_per_warp = qdepth * 32 * qwords * (int) sizeof(T);
   o += kWarpsPerBlock * p.queue_per_warp;
+  o += 4 * 32 * qwords * (int) sizeof(T);       // the four-entry drain reads (and ignores) up to three slots past a queue
   p.total = o;
   return p;
 }
@@ -277,8 +279,8 @@ __device__ __forceinline__ void hist_add(const BlockCtx<T> &C, int bin, T w) {
 // warps keep counting because every word is taken with an atomic exchange.
 __device__ __forceinline__ void sweep_hist(unsigned int *h, unsigned long long *g, int ntot, int lane) {
   for (int i = lane; i < ntot; i += 32) {
-    unsigned int v = atomicExch(&h[i], 0u);
-    if (v) atomicAdd(&g[i], (unsigned long long) v);
+    const int v = (int) atomicExch(&h[i], 0u);  // signed: a pending correction of the fast drain may leave -1 behind
+    if (v) atomicAdd(&g[i], (unsigned long long) (long long) v);
   }
 }
 
@@ -414,90 +416,97 @@ __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x);
 // Fast bins of a box / isotropic pair from ONE approximate reciprocal square root r = rsqrt(d2):
 //   s        = d2 * r            -> s bin  floor(s)   (floor(sqrt(floor(d2))) == floor(sqrt(d2)) exactly)
 //   nmu * mu = nmu * |dz| * r    -> mu bin floor(.)   (== floor(sqrt(floor(fl(fl(dz2/d2)*nmu^2)))) away from bin edges)
-// Both are computed scaled by 4096 and truncated by adding 2^23 toward zero: the mantissa then holds
-// floor(4096 x) = bin * 4096 + 12 fraction bits.  The approximations (rsqrt.approx 2^-22 rel., three multiplies)
-// move s by < 40 * 5e-7 and nmu*mu by < 255 * 5e-7, the reference's own roundings move nmu*mu by < 255 * 1.8e-7,
-// all far below 2^-12: a pair whose fraction bits are 0x000 or 0xFFF (within 2^-12 of a bin edge), d2 < EPS or
-// mu >= 1 is flagged and re-binned by the caller with the exact IEEE sequence (bin_entry).
-// Fast bins of a box / isotropic pair from ONE approximate reciprocal square root r = rsqrt(d2):
-//   s        = d2 * r            -> s bin  floor(s)   (floor(sqrt(floor(d2))) == floor(sqrt(d2)) exactly)
-//   nmu * mu = nmu * |dz| * r    -> mu bin floor(.)   (== floor(sqrt(floor(fl(fl(dz2/d2)*nmu^2)))) away from bin edges)
 // Both are computed scaled by 2^ks / 2^km (chosen on the host from ns / nmu) and truncated by adding 2^23 toward
 // zero: the mantissa then holds floor(2^k x) + 1 = bin * 2^k + k fraction bits (the +1 rides on the FFMA).
 // Error budget: rsqrt.approx 2^-22 rel. + two roundings move s by < ns * 3e-7; the same plus the reference's own
 // three roundings move nmu*mu by < nmu * 4.5e-7; the host picks 2^-ks >= 2.5 * ns * 3e-7 and 2^-km >= 2.2 * nmu * 4.5e-7.
-// A pair is flagged (re-binned with the exact IEEE sequence by the caller) when
+// A pair must be re-binned with the exact IEEE sequence when
 //   s  : fraction bits in {2^ks - 1, 0, 1, 2}  -> s within [-1, 3) / 2^ks of an edge; also catches d2 < EPS (s ~ 0)
 //   mu : fraction bits in {2^km - 1, 0}        -> nmu*mu within [-1, 1) / 2^km of an integer; also catches mu >= 1,
 //        since nmu*mu cannot exceed nmu by more than the error budget.
-// Integer work is kept off the half-rate ALU pipe where possible (IMAD.HI shifts, one IMAD + one compare for the test).
-// Returns the bin biased by bias_s + bias_m * ns, where bias = 0x4B000000 >> k; the caller folds it into the base address.
+// `t` (output) is zero for such a pair: the product of the masked fraction bits (it may also wrap to zero, which
+// only costs a needless exact evaluation).  Integer work is kept off the half-rate ALU pipe where possible
+// (IMAD.HI shifts, IMAD product).  Returns the bin biased by bias_s + bias_m * ns, bias = 0x4B000000 >> k; the
+// caller folds the bias into the base address.  The biased bin of ANY pair that passed the range test lies in
+// [bias, bias + ntot + ns]: s <= ns (1 + 3e-7), nmu*mu <= nmu (1 + 4.5e-7).
 template <int BIN>
 __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale, const float mscale_nmu,
                                          const unsigned int smask, const unsigned int mmask,
-                                         const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, bool &amb) {
+                                         const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, unsigned int &t) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2 + 1e-30f));      // d2 = 0 (coincident points): finite r, s = 0 -> flagged
   const unsigned int us = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(d2 * r, sscale, 1.0f), 8388608.0f));
-  unsigned int t = us & smask;
+  t = us & smask;
   int bin = (int) __umulhi(us, sshift_mul);     // us >> ks
   if (BIN == BIN_SMU) {
     const unsigned int um = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(fabsf(dz) * r, mscale_nmu, 1.0f), 8388608.0f));
-    t *= (um & mmask);                          // (may wrap to 0: a spurious flag is harmless)
+    t *= (um & mmask);
     bin += (int) __umulhi(um, mshift_mul) * ns; // (um >> km) * ns
   }
-#if FCFC_ABLATE == 3            /* experiment: never re-bin exactly (results not exact) */
-  amb = false;
-#else
-  amb = (t == 0u);
-#endif
   return bin;
 }
 
-// Exact re-binning of a flagged pair, out of line (rare): keeps its registers and code out of the drain loop.
-// Tables are read from global memory (P.stab / P.mutab), which is fine at this frequency.
+__device__ __forceinline__ void red_shared_u32_add(unsigned a, unsigned v) {
+  asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v));
+}
+
+// Exact re-binning of one flagged pair, out of line (a few pairs per ten thousand): keeps its registers and code
+// out of the drain loop.  Tables are read from global memory (P.stab / P.mutab), which is fine at this frequency.
+// Unweighted counts were already added to the fast bin by the drain loop: that increment is taken back here
+// (the 32-bit shared counters are signed, see sweep_hist).
 template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
-__device__ __noinline__ int rebin_exact(const CountParams<T> &P, T e0, T e1) {
+__device__ __noinline__ void fix_entry(const CountParams<T> &P, unsigned int hist_s, unsigned int hstride, unsigned int hlane,
+                                       unsigned int qaddr) {
   BlockCtx<T> G;
   G.hist_u = nullptr; G.hist_d = nullptr; G.blk_evals = nullptr;
   G.stab = P.stab; G.ptab = P.ptab; G.mutab = P.mutab; G.s2bin = P.s2bin; G.pbin = P.pbin;
   T e[NW], w;
-  e[0] = e0; e[1 % NW] = e1;
-  return bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
+  QOps<T, NW>::load(qaddr, e);
+  const int b = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
+  if (WT) { if (b >= 0) red_shared_f64(hist_s + hlane + hstride * (unsigned int) b, (double) w, true); }
+  else {
+    const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
+    unsigned int t;
+    const int fb = fast_bins<BIN>(to_f32(e[0]), (BIN == BIN_SMU) ? to_f32(e[1 % NW]) : 0.0f, P.fb_sscale, P.fb_mscale, P.fb_smask,
+                                  P.fb_mmask, 1u << (32 - P.fb_sshift), 1u << (32 - P.fb_mshift), P.ns, t) - bias;
+    if (b != fb) {
+      red_shared_u32_add(hist_s + 4u * (unsigned int) fb, 0xffffffffu);
+      if (b >= 0) red_shared_u32_add(hist_s + 4u * (unsigned int) b, 1u);
+    }
+  }
 }
 
 // Drain of the fast variants whose bins are computed (box (s,mu) or isotropic counts, integer tables that are
 // floor(sqrt(i)), zero lower bounds, shared-memory histogram): every lane pops `rounds` entries off its stack,
-// two per iteration.  While all lanes still have entries (FULL) nothing is predicated; the ragged tail, where
-// some lanes have run dry, predicates the histogram update.  Pairs flagged by fast_bins are re-binned exactly.
-template <class T, int BIN, bool WT, int NW, bool FULL, int NE>
-__device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, const unsigned int HS, unsigned int &rp,
-                                                int k0, int k1, int mine, unsigned int &flagged) {
+// four per iteration, with no data-dependent branch.  Unweighted: every popped pair increments its fast bin
+// unconditionally (FULL: all lanes still have entries; otherwise lanes that have run dry aim at a private dump
+// slot); weighted: predicated.  One bit per pair records whether it was clean (carry chain:
+// clean = 2 * clean + (t != 0), two instructions); the rare other pairs are re-binned exactly after the loop.
+template <class T, int BIN, bool WT, int NW, bool FULL>
+__device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, const unsigned int HS, const unsigned int dump,
+                                                unsigned int &rp, int k0, int k1, int mine, unsigned int &clean) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  constexpr int NE = 4;
   const float sscale = P.fb_sscale, mscale = P.fb_mscale;
   const unsigned int smask = P.fb_smask, mmask = P.fb_mmask, smul = 1u << (32 - P.fb_sshift), mmul = 1u << (32 - P.fb_mshift);
-  // NE independent entries per iteration and no data-dependent branch: flagged entries are only recorded
-  // (one bit per round) and re-binned after the loop.
 #pragma unroll 1
   for (int k = k0; k < k1; k += NE, rp += NE * S) {
     T e[NE][NW];
 #pragma unroll
     for (int i = 0; i < NE; i++) QOps<T, NW>::load(rp + i * S, e[i]);   // slots above the old top hold stale entries: ignored
-    const unsigned int kbit = 1u << k;
 #pragma unroll
     for (int i = 0; i < NE; i++) {
-      bool amb;
+      unsigned int t;
       const int bin = fast_bins<BIN>(to_f32(e[i][0]), (BIN == BIN_SMU) ? to_f32(e[i][1 % NW]) : 0.0f, sscale, mscale, smask,
-                                     mmask, smul, mmul, P.ns, amb);
+                                     mmask, smul, mmul, P.ns, t);
       const bool h = FULL || (k + i < mine);
-      if (amb && h) flagged |= kbit << i;
-      const unsigned int addr = hist_adj + HS * (unsigned int) bin;
-#if FCFC_ABLATE == 2            /* experiment: binning without the histogram update */
-      if (bin == 0x7fffffff) red_shared_u32(addr, h && !amb);
-#else
-      if (WT) red_shared_f64(addr, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h && !amb);
-      else red_shared_u32(addr, h && !amb);
-#endif
+      unsigned int addr = hist_adj + HS * (unsigned int) bin;
+      if (WT) red_shared_f64(addr, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h && t != 0u);
+      else {
+        if (!FULL) addr = h ? addr : dump;
+        red_shared_u32_add(addr, 1u);
+      }
+      asm("{.reg .u32 tmp; add.cc.u32 tmp, %1, 0xffffffff; addc.u32 %0, %0, %0;}" : "+r"(clean) : "r"(t));
     }
   }
 }
@@ -506,32 +515,25 @@ template <class T, int BIN, bool BOX, bool WT, int ARITH, int NW>
 __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockCtx<T> &C, const FastCtx &F,
                                            LaneQueue<T, NW> &Q, int rounds) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  const int mine = min((int) (Q.fill_bytes() / S), rounds);     // entries this lane pops (rounds <= 32)
+  const int mine = min((int) (Q.fill_bytes() / S), rounds);     // entries this lane pops (rounds <= 32, a multiple of 4)
   Q.top -= (unsigned int) mine * S;
   unsigned int rp = Q.top;
   const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
   const unsigned int hs = WT ? F.hstride : 4u;
   const unsigned int hist_adj = F.hist_s + (WT ? F.hlane : 0u) - hs * (unsigned int) bias;
+  const unsigned int dump = F.hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (threadIdx.x & 31u);
   const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;  // rounds in which every lane still has four entries
-#if FCFC_ABLATE == 1            /* experiment: pop without binning */
-  if (P.ns > 0) return;
-#endif
-  unsigned int flagged = 0;     // bit k: the entry of round k must be re-binned exactly
-  drain_fast_loop<T, BIN, WT, NW, true, 4>(P, hist_adj, hs, rp, 0, nfull, mine, flagged);
-  drain_fast_loop<T, BIN, WT, NW, false, 2>(P, hist_adj, hs, rp, nfull, rounds, mine, flagged);
-  while (__any_sync(0xffffffffu, flagged != 0)) {               // rare: a few entries per thousand
-    if (flagged) {
-      const int k = __ffs((int) flagged) - 1;
-      flagged &= flagged - 1;
-      T e[NW];
-      QOps<T, NW>::load(Q.top + (unsigned int) k * S, e);
-      const int b = rebin_exact<T, BIN, BOX, WT, ARITH, NW>(P, e[0], e[1 % NW]);
-      if (b >= 0) {
-        if (WT) red_shared_f64(F.hist_s + F.hlane + F.hstride * (unsigned int) b, (double) e[(BIN == BIN_ISO) ? 1 % NW : 2 % NW], true);
-        else red_shared_u32(F.hist_s + 4u * (unsigned int) b, true);
-      }
-    }
+  unsigned int clean = 0;       // one bit per round, most recent round in bit 0
+  drain_fast_loop<T, BIN, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
+  drain_fast_loop<T, BIN, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
+  unsigned int flagged = ~clean & (0xffffffffu >> (32 - rounds));
+  while (flagged) {                                             // rare
+    const int k = rounds - __ffs((int) flagged);
+    flagged &= flagged - 1;
+    if (k < mine)                                               // (stale entries past this lane's stack may have raised a flag)
+      fix_entry<T, BIN, BOX, WT, ARITH, NW>(P, F.hist_s, F.hstride, F.hlane, Q.top + (unsigned int) k * S);
   }
+  __syncwarp();
 }
 
 // Drain of the fast variants that look their bins up: box (s_perp, pi), or integer tables that are not
@@ -595,12 +597,27 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
   const int mx = (int) (__reduce_max_sync(0xffffffffu, Q.fill_bytes()) / S);
   if (mx + need <= P.qdepth - 1) return mx;
-  const int rounds = min(mx - keep, 32);        // (the fast drain records flagged rounds in a 32-bit mask)
+  const int rounds = min((mx - keep + 3) & ~3, 32);     // a multiple of 4 (the fast drain pops four entries per iteration)
+  if (rounds <= 0) return 0;
   if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) {
     if (BIN != BIN_SPI && P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
     else drain_lut<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
   } else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
-  return mx - rounds;
+  return max(mx - rounds, 0);
+}
+
+// Tile point held by `lane` as its r-th primary.
+#ifndef FCFC_LANEMAP
+#define FCFC_LANEMAP 0
+#endif
+__device__ __forceinline__ int tile_slot(int r, int lane) {
+#if FCFC_LANEMAP == 1
+  return r * 32 + ((r & 1) ? 31 - lane : lane);
+#elif FCFC_LANEMAP == 2
+  return r * 32 + ((lane + 11 * r) & 31);
+#else
+  return r * 32 + lane;
+#endif
 }
 
 // One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane,
@@ -610,7 +627,7 @@ template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, int R, b
 __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW> &Q, int &ub,
                                         const Vec4<T> *sbuf, const T *wbuf, int j0, int nj,
                                         const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX], const T (&as)[RMAX],
-                                        const T (&aw)[RMAX], int jglob0, int iglob0) {
+                                        const T (&aw)[RMAX], int jglob0, int iglob0, int lane) {
   const int room = P.qdepth - 1 - R;            // `ub` (warp-uniform bound of the fullest queue) must stay <= room
   int j = j0;
 #pragma unroll 2
@@ -624,7 +641,7 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
     for (int r = 0; r < R; r++) {
       T d2, aux;
       bool ok = eval_pair<T, BIN, BOX, ARITH, GENERIC>(P, ax[r], ay[r], az[r], as[r], b, d2, aux);
-      if (SELF) ok = ok && (jglob0 + j > iglob0 + r * 32);      // unordered pairs once: metric_common.c:2017-2018
+      if (SELF) ok = ok && (jglob0 + j > iglob0 + tile_slot(r, lane));    // unordered pairs once: metric_common.c:2017-2018
       T e[NW];
       if (BIN == BIN_ISO) { e[0] = d2; if (WT) e[1 % NW] = Ar<T>::mul(aw[r], bw); }
       else if (BOX) { e[0] = d2; e[1 % NW] = aux; if (WT) { e[2 % NW] = Ar<T>::mul(aw[r], bw); e[3 % NW] = 0; } }
@@ -660,7 +677,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   // ---- block prologue: zero the histogram, stage tables / edges / stencil rows ----
   if (SMEMHIST) {
     if (WT) for (int i = threadIdx.x; i < P.ntot * hcopies; i += kThreads) C.hist_d[i] = 0.0;
-    else for (int i = threadIdx.x; i < P.ntot; i += kThreads) C.hist_u[i] = 0u;
+    else for (int i = threadIdx.x; i < P.ntot + P.ns + 33; i += kThreads) C.hist_u[i] = 0u;
   }
   if (!P.tabs_global) {
     for (int i = threadIdx.x; i < P.nstab * (P.swidth ? 2 : 1); i += kThreads) s_stab[i] = P.stab[i];
@@ -709,7 +726,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     T px[RMAX], py[RMAX], pz[RMAX], ps[RMAX], pw[RMAX];
 #pragma unroll
     for (int r = 0; r < RMAX; r++) {
-      const int k = r * 32 + lane;
+      const int k = tile_slot(r, lane);
       if (k < cnt) {
         Vec4<T> v = P.pos1[t0 + k];
         px[r] = v.x; py[r] = v.y; pz[r] = v.z; ps[r] = v.s;
@@ -738,7 +755,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           unsigned int add = (unsigned int) (piece_end - b) * (unsigned int) cnt, old = 0;
           if (lane == 0) old = atomicAdd(C.blk_evals, add);
           old = __shfl_sync(0xffffffffu, old, 0);
-          if (old + add >= 0x80000000u || old + add < old) {
+          if (old + add >= 0x40000000u || old + add < old) {
             if (lane == 0) atomicExch(C.blk_evals, 0u);
             sweep_hist(C.hist_u, P.ghist_i, P.ntot, lane);
           }
@@ -762,7 +779,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
-#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0 + lane)
+#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane)
           for (int j = 0;;) {
             if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
             else if (RMAX == 4) {
@@ -830,7 +847,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
         if (v != 0.0) atomicAdd(&P.ghist_d[i], v);
       }
     } else {
-      for (int i = threadIdx.x; i < P.ntot; i += kThreads) { unsigned int v = C.hist_u[i]; if (v) atomicAdd(&P.ghist_i[i], (unsigned long long) v); }
+      for (int i = threadIdx.x; i < P.ntot; i += kThreads) { const int v = (int) C.hist_u[i]; if (v) atomicAdd(&P.ghist_i[i], (unsigned long long) (long long) v); }
     }
   }
   // pair-evaluation counter: one atomic per warp
