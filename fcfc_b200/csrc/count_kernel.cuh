@@ -44,6 +44,10 @@ enum { ARITH_SCALAR = 0, ARITH_FMA = 1 };
 #endif
 template <class T> struct BlockShape { static constexpr int kWarps = (sizeof(T) == 4) ? FCFC_WARPS_F32 : 16; static constexpr int kThreads = kWarps * 32; };
 constexpr int kMaxRows = 1024;          // stencil rows kept in shared memory
+#ifndef FCFC_EVAL_UNROLL
+#define FCFC_EVAL_UNROLL 1
+#endif
+constexpr int kEvalUnroll = FCFC_EVAL_UNROLL;   // secondary points per iteration of the pair loop
 constexpr int kSegPieceMax = 1 << 19;   // secondary points per overflow-accounting piece
 
 template <class T> struct Vec4;
@@ -110,7 +114,7 @@ template <class T> struct CountParams {
   int isauto;
   int tabs_global;                      // lookup tables too large for shared memory: read them from global memory
   int hist_copies;                      // weighted shared-memory histogram: 32 lane-private copies (few bins) or 1
-  int qdepth;                           // entries per lane of the accepted-pair queues (power of two)
+  int qdepth;                           // entries per lane of the accepted-pair queues (a multiple of 4)
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
   unsigned long long *gevals;           // [0] candidate pair evaluations
@@ -522,7 +526,11 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
   const unsigned int hs = WT ? F.hstride : 4u;
   const unsigned int hist_adj = F.hist_s + (WT ? F.hlane : 0u) - hs * (unsigned int) bias;
   const unsigned int dump = F.hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (threadIdx.x & 31u);
+#if FCFC_ABLATE == 5            /* experiment: one drain loop (ragged form) for everything */
+  const int nfull = 0;
+#else
   const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;  // rounds in which every lane still has four entries
+#endif
   unsigned int clean = 0;       // one bit per round, most recent round in bit 0
   drain_fast_loop<T, BIN, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
   drain_fast_loop<T, BIN, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
@@ -606,19 +614,8 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   return max(mx - rounds, 0);
 }
 
-// Tile point held by `lane` as its r-th primary.
-#ifndef FCFC_LANEMAP
-#define FCFC_LANEMAP 0
-#endif
-__device__ __forceinline__ int tile_slot(int r, int lane) {
-#if FCFC_LANEMAP == 1
-  return r * 32 + ((r & 1) ? 31 - lane : lane);
-#elif FCFC_LANEMAP == 2
-  return r * 32 + ((lane + 11 * r) & 31);
-#else
-  return r * 32 + lane;
-#endif
-}
+// Tile point held by `lane` as its r-th primary (other assignments, e.g. reversed in odd r, measured no better).
+__device__ __forceinline__ int tile_slot(int r, int lane) { return r * 32 + lane; }
 
 // One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane,
 // starting at staged point j0.  Returns nj when the chunk is done, or the index of the point at which
@@ -628,12 +625,13 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
                                         const Vec4<T> *sbuf, const T *wbuf, int j0, int nj,
                                         const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX], const T (&as)[RMAX],
                                         const T (&aw)[RMAX], int jglob0, int iglob0, int lane) {
-  const int room = P.qdepth - 1 - R;            // `ub` (warp-uniform bound of the fullest queue) must stay <= room
+  // as many points as cannot overflow the fullest queue even if every pair is accepted: no test inside the loop
+  const int steps = min(nj - j0, (P.qdepth - 1 - ub) / R);
+  ub += steps * R;
+  const int jend = j0 + steps;
   int j = j0;
-#pragma unroll 2
-  for (; j < nj; j++) {
-    if (ub > room) break;
-    ub += R;
+#pragma unroll kEvalUnroll
+  for (; j < jend; j++) {
     const Vec4<T> b = sbuf[j];
     T bw = (T) 1;
     if (WT) bw = wbuf[j];

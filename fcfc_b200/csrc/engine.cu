@@ -677,7 +677,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
     if (ks < 6 || km < 6) P.stab_is_sqrt = 0;   // too many bins for the fixed-point trick: use the exact path
   }
-  // accepted-pair queues: the deepest power-of-two depth that fits next to the histogram and tables
+  // accepted-pair queues: the deepest depth (a multiple of 4, <= 64) that fits next to the histogram and tables
   const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
   // weighted sums with few bins: 32 lane-private copies of the shared histogram, so that the FP64 (CAS) atomics
   // of the lanes of a warp never collide on a bin
@@ -688,7 +688,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
                   : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
   };
   int qdepth_max = 64;
-  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd));
+  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd) & ~3);
   // preference order: everything in shared memory with deep queues > tables in global memory >
   // shallow queues > histogram in global memory (large tables / histograms are rare)
   SmemPlan pl; int depth = 0; bool tabs_global = false; v.smem_hist = true;
@@ -702,7 +702,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   for (auto &t : tries) {
     if (force_ghist && t.sh) continue;
     if (tables_unused && !t.tg && t.sh) continue;       // computed bins: deeper stacks beat resident tables
-    for (int d = qdepth_max; d >= t.dmin && !depth; d >>= 1) {
+    for (int d = qdepth_max; d >= t.dmin && !depth; d -= 4) {
       pl = plan(t.sh, d, t.tg);
       if (pl.total + 1024 <= smem_max) { depth = d; v.smem_hist = t.sh; tabs_global = t.tg; }
     }
