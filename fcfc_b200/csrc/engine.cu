@@ -304,7 +304,7 @@ __global__ void items_kernel(const int *cell_start, const int *tile_off, int nce
 // order, which balances clustered catalogues across warps and across GPUs.
 __global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int ntile, int nsplit, const int *cell_start2,
                                  const int4 *rows, int nrows, int ncx, int ncy, int ncz, int periodic, int isauto,
-                                 float *cost, int *index) {
+                                 unsigned int keep_mask, float *cost, int *index) {
   int it = blockIdx.x * blockDim.x + threadIdx.x;
   if (it >= ntile * nsplit) return;
   const int tile = it / nsplit, split = it - tile * nsplit;
@@ -333,7 +333,9 @@ __global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int 
     const int rowbase = (jx * ncy + jy) * ncz;
     tot += cell_start2[rowbase + zhi + 1] - cell_start2[rowbase + zlo];
   }
-  cost[it] = (float) tot * (float) item_cnt[tile] + 1.0f;
+  // coarse cost classes (exponent + a few mantissa bits): the stable sort keeps the cell order inside a class,
+  // so that warps working at the same time sweep neighbouring cells (L2 reuse of the secondary catalogue)
+  cost[it] = __uint_as_float(__float_as_uint((float) tot * (float) item_cnt[tile] + 1.0f) & keep_mask);
   index[it] = it;
 }
 
@@ -605,9 +607,12 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     auto fail = [&](const char *what) { pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp); pool_free(d_order); pool_free(dbuf); set_err("%s", what); return FCFC_GPU_ERR_TREE; };
     if (pool_alloc(&cost, (size_t) ni * 4) || pool_alloc(&cost2, (size_t) ni * 4) || pool_alloc(&idx, (size_t) ni * 4) ||
         pool_alloc(&d_order, (size_t) ni * 4)) return fail("out of device memory for the work-item order");
+    int cost_bits = 1;            // mantissa bits of the cost classes (experiment hook: 23 = exact cost order)
+    if (const char *ecb = getenv("FCFC_GPU_COST_BITS")) cost_bits = std::max(0, std::min(23, atoi(ecb)));
+    const unsigned int keep_mask = 0xffffffffu << (23 - cost_bits);
     if (ni) {
       item_cost_kernel<<<(ni + 255) / 256, 256>>>(S1.item_cell, S1.item_cnt, S1.nitem, nsplit, S2.cell_start, reinterpret_cast<const int4 *>(dbuf + o_rows),
-                                                  (int) rows.size(), g.nc[0], g.nc[1], g.nc[2], b->periodic, isauto, cost, idx);
+                                                  (int) rows.size(), g.nc[0], g.nc[1], g.nc[2], b->periodic, isauto, keep_mask, cost, idx);
       g_stats.kernel_launches++;
       size_t tb = 0;
       if (cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, cost, cost2, idx, d_order, ni) != cudaSuccess) return fail("cub sort failed");
