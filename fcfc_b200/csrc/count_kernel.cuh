@@ -229,7 +229,7 @@ __device__ __forceinline__ int finish_pair(const CountParams<T> &P, const BlockC
 // First half: distances and the cheap range test.  Outputs d2 and aux as described above.
 template <class T, int BIN, bool BOX, int ARITH, bool GENERIC>
 __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T az, T as,
-                                          const Vec4<T> &b, T &d2, T &aux) {
+                                          const Vec4<T> &b, const T s2lim, T &d2, T &aux) {
   using A = Ar<T>;
   bool ok;
   if (BOX || BIN == BIN_ISO) {
@@ -237,7 +237,7 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
     if (BIN == BIN_SPI) {                       // box (s_perp, pi): metric_common.c:157-165, 416-424
       aux = A::abs(dz);
       d2 = (ARITH == ARITH_SCALAR) ? A::add(A::mul(dx, dx), A::mul(dy, dy)) : A::fma(dy, dy, A::mul(dx, dx));
-      ok = (aux < P.pmax) && (d2 < P.s2max);
+      ok = (aux < P.pmax) && (d2 < s2lim);
       if (GENERIC) ok = ok && (P.pmin0 || aux >= P.pmin);
     } else {
       T dz2 = A::mul(dz, dz);
@@ -245,7 +245,7 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
       else if (BOX) d2 = A::fma(dy, dy, A::fma(dx, dx, dz2));                                   // :426-430
       else d2 = A::fma(dz, dz, A::fma(dy, dy, A::mul(dx, dx)));                                 // 2pt/:330-333
       aux = (BOX && BIN == BIN_SMU) ? dz : dz2;
-      ok = d2 < P.s2max;
+      ok = d2 < s2lim;
     }
   } else {                                      // survey (s,mu) / (s_perp,pi): 2pt/metric_common.c:169-172, 341-357
     T t;
@@ -254,7 +254,7 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
     T s = A::add(as, b.s);
     d2 = A::sub(s, t);
     aux = t;
-    ok = d2 < ((BIN == BIN_SPI) ? P.premax : P.s2max);
+    ok = d2 < s2lim;                            // survey (s_perp, pi): s2max + p2max, see engine.cu
     if (BIN == BIN_SPI) {
       // cheap necessary condition for pi^2 = d*d / (s + t) < p2max, without the division (the exact test is
       // repeated in finish_pair): d*d < (s + t) * p2max * (1 + 8 eps).  Cuts the queue traffic of survey
@@ -614,6 +614,15 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   return max(mx - rounds, 0);
 }
 
+__device__ __forceinline__ void lds_vec4_raw(unsigned a, float &x, float &y, float &z, float &w) {
+  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+}
+__device__ __forceinline__ void lds_vec4_raw(unsigned a, double &x, double &y, double &z, double &w) {
+  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+  asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(z), "=d"(w) : "r"(a));
+}
+template <class T> __device__ __forceinline__ Vec4<T> lds_vec4(unsigned a) { Vec4<T> v; lds_vec4_raw(a, v.x, v.y, v.z, v.s); return v; }
+
 // Tile point held by `lane` as its r-th primary (other assignments, e.g. reversed in odd r, measured no better).
 __device__ __forceinline__ int tile_slot(int r, int lane) { return r * 32 + lane; }
 
@@ -624,21 +633,24 @@ template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, int R, b
 __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW> &Q, int &ub,
                                         const Vec4<T> *sbuf, const T *wbuf, int j0, int nj,
                                         const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX], const T (&as)[RMAX],
-                                        const T (&aw)[RMAX], int jglob0, int iglob0, int lane) {
+                                        const T (&aw)[RMAX], int jglob0, int iglob0, int lane, const T s2lim) {
   // as many points as cannot overflow the fullest queue even if every pair is accepted: no test inside the loop
   const int steps = min(nj - j0, (P.qdepth - 1 - ub) / R);
   ub += steps * R;
   const int jend = j0 + steps;
+  // the staged points are walked with a 32-bit shared-window address (one add per point, no index arithmetic)
+  unsigned int sa = (unsigned int) __cvta_generic_to_shared(sbuf + j0);
+  const unsigned int se = sa + (unsigned int) steps * (unsigned int) sizeof(Vec4<T>);
   int j = j0;
 #pragma unroll kEvalUnroll
-  for (; j < jend; j++) {
-    const Vec4<T> b = sbuf[j];
+  for (; sa != se; sa += (unsigned int) sizeof(Vec4<T>)) {
+    const Vec4<T> b = lds_vec4<T>(sa);
     T bw = (T) 1;
     if (WT) bw = wbuf[j];
 #pragma unroll
     for (int r = 0; r < R; r++) {
       T d2, aux;
-      bool ok = eval_pair<T, BIN, BOX, ARITH, GENERIC>(P, ax[r], ay[r], az[r], as[r], b, d2, aux);
+      bool ok = eval_pair<T, BIN, BOX, ARITH, GENERIC>(P, ax[r], ay[r], az[r], as[r], b, s2lim, d2, aux);
       if (SELF) ok = ok && (jglob0 + j > iglob0 + tile_slot(r, lane));    // unordered pairs once: metric_common.c:2017-2018
       T e[NW];
       if (BIN == BIN_ISO) { e[0] = d2; if (WT) e[1 % NW] = Ar<T>::mul(aw[r], bw); }
@@ -646,7 +658,9 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
       else { e[0] = aux; e[1 % NW] = as[r]; e[2 % NW] = b.s; e[3 % NW] = WT ? Ar<T>::mul(aw[r], bw) : (T) 0; }
       Q.push(e, ok);
     }
+    if (WT || SELF) j++;
   }
+  j = jend;
   return j;
 }
 
@@ -685,7 +699,10 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   for (int i = threadIdx.x; i <= P.ns; i += kThreads) s_s2bin[i] = P.s2bin[i];
   if (BIN == BIN_SPI) for (int i = threadIdx.x; i <= P.np; i += kThreads) s_pbin[i] = P.pbin[i];
   for (int i = threadIdx.x; i < P.nrows; i += kThreads) s_rows[i] = P.rows[i];
-  if (threadIdx.x == 0) *s_blk_evals = 0;
+  if (threadIdx.x == 0) {
+    *s_blk_evals = 0;
+    *reinterpret_cast<T *>(smem + pl.off_misc + 8) = (BIN == BIN_SPI && !BOX) ? P.premax : P.s2max;
+  }
   // queues start zeroed: slots past a queue's tail are read (and ignored) by the two-entry drain
   for (int i = threadIdx.x * 16; i < kWarpsPerBlock * pl.queue_per_warp; i += kThreads * 16)
     *reinterpret_cast<uint4 *>(smem + pl.off_queue + i) = make_uint4(0, 0, 0, 0);
@@ -703,6 +720,9 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   Q.base = Q.top = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue) + warp * (unsigned int) pl.queue_per_warp
                    + lane * (unsigned int) (NW * sizeof(T));
   int ub = 0;                   // warp-uniform upper bound of the fullest lane queue (entries)
+  // upper limit of the range test, parked in a vector register (read back from shared memory, which the compiler
+  // cannot fold into a constant-bank operand: it would otherwise be re-fetched with LDCU for every secondary point)
+  const T s2lim = *reinterpret_cast<volatile T *>(smem + pl.off_misc + 8);
   unsigned long long my_evals = 0;
   const int ncy = P.nc[1], ncz = P.nc[2];
 
@@ -777,7 +797,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
-#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane)
+#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane, s2lim)
           for (int j = 0;;) {
             if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
             else if (RMAX == 4) {
