@@ -488,6 +488,21 @@ static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[
       }
       if (g.nc[d] > 2048) ok = false;
     }
+    if (k == kmin && (!ok || g.ncell() > (1ll << 26))) {
+      // tiny reach in a huge volume: even cells of one reach are too many.  Coarser cells are always valid
+      // (the stencil is derived from the actual cell size).
+      double shrink = 1.0;
+      for (int it = 0; it < 200 && (!ok || g.ncell() > (1ll << 26)); it++) {
+        shrink *= 0.9; ok = true;
+        for (int d = 0; d < 3; d++) {
+          const double ext = b->periodic ? b->bsize[d] : std::max(hi[d] - lo[d], 1e-30);
+          const double want = ((d == 2) ? rz : rxy) / k;
+          int nc = std::max(1, std::min(2048, (int) std::floor(ext / want * shrink) + (b->periodic ? 0 : 1)));
+          g.nc[d] = nc;
+          if (b->periodic) g.cs[d] = ext / nc; else g.cs[d] = std::max(want, ext / nc * (1 + 1e-9));
+        }
+      }
+    }
     if (!ok || g.ncell() > (1ll << 26)) break;
     const double ncell = (double) g.ncell();
     const double m1 = std::max(n1 / ncell, 1e-3), m2 = std::max(n2 / ncell, 1e-3);
