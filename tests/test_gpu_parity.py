@@ -165,6 +165,39 @@ def test_edge_cases(gpu):
                                           oracle.count(ob, oracle.preprocess(ob, cat), oracle.preprocess(ob, ([5.0], [5.0], [5.0]))))
 
 
+@pytest.mark.parametrize("prec", ["double", "float"])
+def test_tiny_reach_in_huge_volume(gpu, prec):
+    """s_max = 2 in a 20000 box (and a sparse survey volume): one reach per cell would need > 2048 cells per axis,
+    the grid falls back to coarser cells.  Pairs are planted so that the histogram is not empty."""
+    rng = np.random.default_rng(77)
+    L = 20000.0
+    x = rng.random((6000, 3)) * L
+    x[1000:2000] = (x[:1000] + rng.normal(0, 0.6, (1000, 3))) % L      # close companions, some across the faces
+    x[:50, 0] = rng.random(50) * 0.5; x[1000:1050, 0] = L - rng.random(50) * 0.5
+    x[1000:1050, 1:] = x[:50, 1:]
+    x = np.round(x, 5); x[x >= L] = 0.0
+    cat = (x[:, 0].copy(), x[:, 1].copy(), x[:, 2].copy())
+    kw = dict(box=L, bintype=1, smax=2.0, ds=0.25, nmu=20)
+    got = gpu_counts(gpu, kw, True, prec, [cat], ["DD"], False)["DD"]
+    ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+    want = oracle.count(ob, oracle.preprocess(ob, cat))
+    assert want.sum() > 500
+    np.testing.assert_array_equal(got, want)
+    if prec == "float":
+        return          # (s1 + s2) - t at |x| ~ 5e4 has no significant digits left in float for s < 2
+    # survey geometry: same idea without periodic images
+    sx, sy, sz, sw = survey_catalog(4000, 78)
+    s = np.stack([sx, sy, sz], 1) * 40.0                               # 40000-68000 Mpc/h: enormous, sparse volume
+    s[2000:] = s[:2000] + rng.normal(0, 0.5, (2000, 3))
+    scat = (s[:, 0].copy(), s[:, 1].copy(), s[:, 2].copy(), sw)
+    kw = dict(bintype=2, smax=2.0, ds=0.25, pmin=0.0, pmax=3.0, dpi=0.5)
+    got = gpu_counts(gpu, kw, False, prec, [scat], ["DD"], True)["DD"]
+    ob = oracle.setup(prec=prec[0], periodic=False, **kw)
+    want = oracle.count(ob, oracle.preprocess(ob, scat), withwt=True)
+    assert (want > 0).sum() > 20
+    assert_counts(got, want, True)
+
+
 def test_huge_histogram_uses_global_path(gpu):
     """ns = 600 x nmu = 255 = 153000 bins do not fit the shared-memory histogram: global-atomic variant."""
     kw = dict(box=500.0, bintype=1, smax=60.0, ds=0.1, nmu=255)
