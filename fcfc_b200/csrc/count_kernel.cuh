@@ -17,11 +17,13 @@
 //   * per pair: 3 subtractions + 1 multiply + 2 FMA (6 FP32 instructions, FMA mode) or
 //     3 sub + 3 mul + 2 add (scalar-parity mode) and one compare.  Pairs that pass the range test
 //     are NOT binned in place (that would leave most lanes idle in a divergent branch): each lane
-//     appends (d^2, aux[, w]) to its own circular queue in shared memory (one predicated store);
-//   * when a queue is nearly full the warp drains: every lane pops its own entries, so all 32
-//     lanes run the expensive part (division for mu, table lookups, shared-memory atomic) together;
-//     the histogram is per block in shared memory (32-bit counters flushed lock-free to 64-bit
-//     global counters; FP64 sums for weighted counts).
+//     pushes (d^2, aux[, w]) on its own stack in shared memory (one predicated store + pointer bump);
+//   * when a stack is nearly full the warp drains: every lane pops its own entries, four per
+//     iteration, so all 32 lanes run the expensive part (bins, histogram update) together.  Box and
+//     isotropic counts compute both bins from one rsqrt.approx with fixed-point edge detection; pairs
+//     within the error band of a bin edge are re-binned with the exact IEEE sequence of the reference
+//     (results are bit-exact).  The histogram is per block in shared memory (32-bit counters flushed
+//     lock-free to 64-bit global counters; FP64 sums for weighted counts).
 //
 // No tensor cores: the work is FP32/FP64 CUDA-core arithmetic plus shared-memory atomics.
 #pragma once
@@ -36,9 +38,6 @@ enum { ARITH_SCALAR = 0, ARITH_FMA = 1 };
 
 // Warps per block (one block per SM): as many as the register file allows -- the kernels are latency bound
 // at 4 warps per scheduler.  float variants fit in 80 registers (24 warps), double variants <= 128 (16 warps).
-#ifndef FCFC_ABLATE
-#define FCFC_ABLATE 0
-#endif
 #ifndef FCFC_WARPS_F32
 #define FCFC_WARPS_F32 24
 #endif
@@ -526,11 +525,8 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
   const unsigned int hs = WT ? F.hstride : 4u;
   const unsigned int hist_adj = F.hist_s + (WT ? F.hlane : 0u) - hs * (unsigned int) bias;
   const unsigned int dump = F.hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (threadIdx.x & 31u);
-#if FCFC_ABLATE == 5            /* experiment: one drain loop (ragged form) for everything */
-  const int nfull = 0;
-#else
-  const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;  // rounds in which every lane still has four entries
-#endif
+  // rounds in which every lane still has four entries (one ragged loop for everything measured 1.5 % slower)
+  const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;
   unsigned int clean = 0;       // one bit per round, most recent round in bit 0
   drain_fast_loop<T, BIN, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
   drain_fast_loop<T, BIN, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
