@@ -419,8 +419,8 @@ __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x);
 // Fast bins of a box / isotropic pair from ONE approximate reciprocal square root r = rsqrt(d2):
 //   s        = d2 * r            -> s bin  floor(s)   (floor(sqrt(floor(d2))) == floor(sqrt(d2)) exactly)
 //   nmu * mu = nmu * |dz| * r    -> mu bin floor(.)   (== floor(sqrt(floor(fl(fl(dz2/d2)*nmu^2)))) away from bin edges)
-// Both are computed scaled by 2^ks / 2^km (chosen on the host from ns / nmu) and truncated by adding 2^23 toward
-// zero: the mantissa then holds floor(2^k x) + 1 = bin * 2^k + k fraction bits (the +1 rides on the FFMA).
+// Both are computed scaled by 2^ks / 2^km (chosen on the host from ns / nmu) and truncated by a fused multiply-add
+// of 2^23 + 1 rounded toward zero: the mantissa then holds floor(2^k x) + 1 = bin * 2^k + k fraction bits.
 // Error budget: rsqrt.approx 2^-22 rel. + two roundings move s by < ns * 3e-7; the same plus the reference's own
 // three roundings move nmu*mu by < nmu * 4.5e-7; the host picks 2^-ks >= 2.5 * ns * 3e-7 and 2^-km >= 2.2 * nmu * 4.5e-7.
 // A pair must be re-binned with the exact IEEE sequence when
@@ -438,11 +438,20 @@ __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale,
                                          const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, unsigned int &t) {
   float r;
   asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2 + 1e-30f));      // d2 = 0 (coincident points): finite r, s = 0 -> flagged
-  const unsigned int us = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(d2 * r, sscale, 1.0f), 8388608.0f));
+  // one fused multiply-add rounded toward zero: the mantissa is exactly floor(2^ks s) + 1
+  float sr, mr = 0.0f;
+  if (BIN == BIN_SMU) {         // (d2, dz) * (r, r) as one packed multiply (sm_100a FMUL2: half the issue slots)
+    unsigned long long e2, r2, p2;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(d2), "f"(dz));
+    asm("mov.b64 %0, {%1, %1};" : "=l"(r2) : "f"(r));
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(e2), "l"(r2));
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(sr), "=f"(mr) : "l"(p2));
+  } else sr = d2 * r;
+  const unsigned int us = (unsigned int) __float_as_int(__fmaf_rz(sr, sscale, 8388609.0f));
   t = us & smask;
   int bin = (int) __umulhi(us, sshift_mul);     // us >> ks
   if (BIN == BIN_SMU) {
-    const unsigned int um = (unsigned int) __float_as_int(__fadd_rz(__fmaf_rn(fabsf(dz) * r, mscale_nmu, 1.0f), 8388608.0f));
+    const unsigned int um = (unsigned int) __float_as_int(__fmaf_rz(fabsf(mr), mscale_nmu, 8388609.0f));
     t *= (um & mmask);
     bin += (int) __umulhi(um, mshift_mul) * ns; // (um >> km) * ns
   }
