@@ -294,6 +294,7 @@ template <class T, int NW> struct QOps;
 // push: predicated store + predicated pointer bump in one asm block (a stack: no wrap-around arithmetic)
 #define FCFC_PUSH_ASM(ST) "{.reg .pred q; setp.ne.s32 q, %1, 0; " ST " @q add.u32 %0, %0, %2;}"
 template <int NW> struct QOps<float, NW> {
+  static __device__ __forceinline__ unsigned lane_offset(int lane) { return (unsigned) lane * (unsigned) (NW * sizeof(float)); }
   static __device__ __forceinline__ void push(unsigned &w, const float (&v)[NW], bool p) {
     constexpr unsigned S = 32u * NW * sizeof(float);
     if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f32 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]));
@@ -307,6 +308,7 @@ template <int NW> struct QOps<float, NW> {
   }
 };
 template <int NW> struct QOps<double, NW> {
+  static __device__ __forceinline__ unsigned lane_offset(int lane) { return (unsigned) lane * (unsigned) (NW * sizeof(double)); }
   static __device__ __forceinline__ void push(unsigned &w, const double (&v)[NW], bool p) {
     constexpr unsigned S = 32u * NW * sizeof(double);
     if (NW == 1) asm volatile(FCFC_PUSH_ASM("@q st.shared.f64 [%0], %3;") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]));
@@ -628,6 +630,30 @@ __device__ __forceinline__ void lds_vec4_raw(unsigned a, double &x, double &y, d
 }
 template <class T> __device__ __forceinline__ Vec4<T> lds_vec4(unsigned a) { Vec4<T> v; lds_vec4_raw(a, v.x, v.y, v.z, v.s); return v; }
 
+// ---------------------------------------------------------------------------------------------
+// Packed FP32 pairs (sm_100a add/mul/fma.rn.f32x2: the lane throughput of the scalar forms at half the issue
+// slots; a scalar operand is broadcast for free).  Every operation is a separate IEEE round-to-nearest
+// instruction, exactly like its scalar counterpart: results are bit-identical.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void upk2(f32x2 v, float &lo, float &hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 d; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) { f32x2 d; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+// Product that must stay a separately rounded product (scalar-parity order): ptxas contracts mul.rn.f32x2 + add.rn.f32x2
+// into FFMA2 (observed in the SASS; a literal -0 addend is folded away first), unlike the scalar forms.
+// x * y + (-0) with a -0 that ptxas cannot see through (read from shared memory at kernel start) is the correctly
+// rounded product and leaves nothing to contract.
+__device__ __forceinline__ f32x2 mul2_uncontracted(f32x2 a, f32x2 b, float negzero) { return fma2(a, b, pk2(negzero, negzero)); }
+
+// Variants whose pair loop runs packed: float, isotropic bins, unweighted (one word per queue entry).  Their staging
+// buffer holds the 32 secondary points as 16 pairs, [pair][x0 x1 y0 y1 z0 z1 - -] (32 bytes per pair).  With two-word
+// entries ((s,mu), (s_perp,pi)) the packed results (d2_0, d2_1), (dz_0, dz_1) would have to be re-paired for the
+// 64-bit push: measured slower than the scalar loop (474 vs 460 ms on the bench workload; two 32-bit pushes: 467 ms).
+template <class T, int BIN, bool BOX, bool WT> struct PairLoop { static constexpr bool kPacked = sizeof(T) == 4 && BIN == BIN_ISO && !WT; };
+__device__ __forceinline__ unsigned staged_pair_addr(unsigned sbuf_s, int j) { return sbuf_s + (unsigned) (j >> 1) * 32u + (unsigned) (j & 1) * 4u; }
+
 // Tile point held by `lane` as its r-th primary (other assignments, e.g. reversed in odd r, measured no better).
 __device__ __forceinline__ int tile_slot(int r, int lane) { return r * 32 + lane; }
 
@@ -638,7 +664,52 @@ template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, int R, b
 __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW> &Q, int &ub,
                                         const Vec4<T> *sbuf, const T *wbuf, int j0, int nj,
                                         const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX], const T (&as)[RMAX],
-                                        const T (&aw)[RMAX], int jglob0, int iglob0, int lane, const T s2lim) {
+                                        const T (&aw)[RMAX], int jglob0, int iglob0, int lane, const T s2lim, const float negzero) {
+  constexpr bool kPacked = PairLoop<T, BIN, BOX, WT>::kPacked;
+  const unsigned int sbuf_s = (unsigned int) __cvta_generic_to_shared(sbuf);
+  if constexpr (kPacked && !SELF) {
+    // two secondary points per step: as many steps as cannot overflow the fullest queue even if every pair is accepted
+    const int steps = min((nj - j0 + 1) >> 1, (P.qdepth - 1 - ub) / (2 * R));
+    ub += steps * 2 * R;
+    unsigned int sa = sbuf_s + (unsigned int) (j0 >> 1) * 32u;     // j0 is even: this path always advances by pairs
+    const unsigned int se = sa + (unsigned int) steps * 32u;
+#pragma unroll kEvalUnroll
+    for (; sa != se; sa += 32u) {
+      f32x2 X, Y, Z;
+      asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
+      asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
+#pragma unroll
+      for (int r = 0; r < R; r++) {
+        const f32x2 dx = sub2(pk2(ax[r], ax[r]), X), dy = sub2(pk2(ay[r], ay[r]), Y), dz = sub2(pk2(az[r], az[r]), Z);
+        f32x2 d2, aux;
+        if (BIN == BIN_SPI) {                     // box (s_perp, pi): metric_common.c:157-165, 416-424
+          d2 = (ARITH == ARITH_SCALAR) ? add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)) : fma2(dy, dy, mul2(dx, dx));
+          aux = dz;
+        } else {
+          const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
+          if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
+          else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
+          else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
+          aux = (BOX && BIN == BIN_SMU) ? dz : dz2;
+        }
+        float d2h[2], auxh[2];
+        upk2(d2, d2h[0], d2h[1]); upk2(aux, auxh[0], auxh[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          if (BIN == BIN_SPI) auxh[h] = fabsf(auxh[h]);
+          bool ok = d2h[h] < s2lim;
+          if (BIN == BIN_SPI) ok = ok && (auxh[h] < P.pmax);
+          if (GENERIC) ok = ok && (P.smin0 || d2h[h] >= P.s2min);
+          if (GENERIC && BIN == BIN_SPI) ok = ok && (P.pmin0 || auxh[h] >= P.pmin);
+          T e[NW];
+          e[0] = d2h[h];
+          if (BIN != BIN_ISO) e[1 % NW] = auxh[h];
+          Q.push(e, ok);
+        }
+      }
+    }
+    return min(j0 + 2 * steps, nj);
+  }
   // as many points as cannot overflow the fullest queue even if every pair is accepted: no test inside the loop
   const int steps = min(nj - j0, (P.qdepth - 1 - ub) / R);
   ub += steps * R;
@@ -649,7 +720,14 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
   int j = j0;
 #pragma unroll kEvalUnroll
   for (; sa != se; sa += (unsigned int) sizeof(Vec4<T>)) {
-    const Vec4<T> b = lds_vec4<T>(sa);
+    Vec4<T> b;
+    if constexpr (kPacked) {      // (only the tile against its own points gets here: SELF) pair layout, one point
+      const unsigned int pa = staged_pair_addr(sbuf_s, j);
+      asm("ld.shared.f32 %0, [%1];" : "=f"(b.x) : "r"(pa));
+      asm("ld.shared.f32 %0, [%1+8];" : "=f"(b.y) : "r"(pa));
+      asm("ld.shared.f32 %0, [%1+16];" : "=f"(b.z) : "r"(pa));
+      b.s = 0;
+    } else b = lds_vec4<T>(sa);
     T bw = (T) 1;
     if (WT) bw = wbuf[j];
 #pragma unroll
@@ -674,6 +752,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   extern __shared__ __align__(16) unsigned char smem[];
   constexpr int kThreads = BlockShape<T>::kThreads, kWarpsPerBlock = BlockShape<T>::kWarps;
   constexpr int NW = QFmt<BIN, BOX, WT>::NW;
+  constexpr bool kPacked = PairLoop<T, BIN, BOX, WT>::kPacked;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
   const SmemPlan pl = make_smem_plan<T, WT>(P.ntot, P.nstab * (P.swidth ? 2 : 1), P.nptab * (P.pwidth ? 2 : 1),
@@ -707,6 +786,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   if (threadIdx.x == 0) {
     *s_blk_evals = 0;
     *reinterpret_cast<T *>(smem + pl.off_misc + 8) = (BIN == BIN_SPI && !BOX) ? P.premax : P.s2max;
+    *reinterpret_cast<float *>(smem + pl.off_misc + 4) = -0.0f;
   }
   // queues start zeroed: slots past a queue's tail are read (and ignored) by the two-entry drain
   for (int i = threadIdx.x * 16; i < kWarpsPerBlock * pl.queue_per_warp; i += kThreads * 16)
@@ -723,11 +803,12 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   T *wbuf = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sbuf) + 32 * sizeof(Vec4<T>));
   LaneQueue<T, NW> Q;
   Q.base = Q.top = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue) + warp * (unsigned int) pl.queue_per_warp
-                   + lane * (unsigned int) (NW * sizeof(T));
+                   + QOps<T, NW>::lane_offset(lane);
   int ub = 0;                   // warp-uniform upper bound of the fullest lane queue (entries)
   // upper limit of the range test, parked in a vector register (read back from shared memory, which the compiler
   // cannot fold into a constant-bank operand: it would otherwise be re-fetched with LDCU for every secondary point)
   const T s2lim = *reinterpret_cast<volatile T *>(smem + pl.off_misc + 8);
+  const float negzero = kPacked ? *reinterpret_cast<volatile float *>(smem + pl.off_misc + 4) : 0.0f;     // see mul2_uncontracted
   unsigned long long my_evals = 0;
   const int ncy = P.nc[1], ncz = P.nc[2];
 
@@ -795,14 +876,20 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
         for (int c0 = b; c0 < piece_end; c0 += 32) {
           __syncwarp();
           if (BOX) { nxt.x = Ar<T>::add(nxt.x, sbx); nxt.y = Ar<T>::add(nxt.y, sby); nxt.z = Ar<T>::add(nxt.z, sbz); }
-          sbuf[lane] = nxt;
+          if constexpr (kPacked) {        // pairs of points; lanes past the end of the range park a point that is never in range
+            const bool live = c0 + lane < piece_end;
+            const unsigned int pa = staged_pair_addr((unsigned int) __cvta_generic_to_shared(sbuf), lane);
+            asm volatile("st.shared.f32 [%0], %1;" ::"r"(pa), "f"(live ? nxt.x : -Ar<T>::far()));
+            asm volatile("st.shared.f32 [%0+8], %1;" ::"r"(pa), "f"(live ? nxt.y : -Ar<T>::far()));
+            asm volatile("st.shared.f32 [%0+16], %1;" ::"r"(pa), "f"(live ? nxt.z : -Ar<T>::far()));
+          } else sbuf[lane] = nxt;
           if (WT) wbuf[lane] = nxtw;
           __syncwarp();
           jn = c0 + 32 + lane;
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
-#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane, s2lim)
+#define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane, s2lim, negzero)
           for (int j = 0;;) {
             if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
             else if (RMAX == 4) {
@@ -815,7 +902,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
             } else j = (nr == 1) ? FCFC_CHUNK(1, false) : FCFC_CHUNK(RMAX, false);
             if (j >= nj) break;
             // a queue may overflow: the one place where queued pairs are binned
-            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, RMAX, P.qdepth / 4);
+            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, kPacked ? 2 * RMAX : RMAX, P.qdepth / 4);
           }
 #undef FCFC_CHUNK
         }

@@ -729,6 +729,9 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     if (depth) break;
   }
   if (!depth) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  // the packed pair loop (float, isotropic, unweighted: 4-byte entries) needs room for 2 x 4 entries above the
+  // quarter that a drain leaves behind
+  if (is_float && bintype == BIN_ISO && !withwt && depth < 12) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan leaves no room for the pair stacks"); return FCFC_GPU_ERR_CF; }
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one

@@ -151,14 +151,16 @@ OVERWRITE = 2
 VERBOSE = F
 """)
         _run(exe, str(conf), str(d))
-    # weighted sums: <= 1e-12 relative on every number of every output table
+    # weighted sums agree to <= 1e-12 relative, but the tables are text with 10 significant digits: a sum that
+    # differs in its 16th digit can still flip the last printed digit.  Every number must agree to one unit of the
+    # last printed digit, and all but a handful (rounding flips) to 1e-12.
     for f in ("DD.bin", "DR.bin", "RR.bin", "xi.txt", "wp.txt"):
         a = np.loadtxt(tmp_path / "ref" / f)
         b = np.loadtxt(tmp_path / "gpu" / f)
         assert a.shape == b.shape
-        np.testing.assert_allclose(b, a, rtol=1e-10, atol=1e-12)
-    # the pair counts themselves (normalised columns) to 1e-12
+        np.testing.assert_allclose(b, a, rtol=1.5e-9, atol=1e-12)
     for f in ("DD.bin", "DR.bin", "RR.bin"):
-        a = np.loadtxt(tmp_path / "ref" / f)
-        b = np.loadtxt(tmp_path / "gpu" / f)
-        np.testing.assert_allclose(b[:, -2:], a[:, -2:], rtol=1e-12, atol=0)
+        a = np.loadtxt(tmp_path / "ref" / f)[:, -2:]
+        b = np.loadtxt(tmp_path / "gpu" / f)[:, -2:]
+        flips = np.abs(b - a) > 1e-12 * np.abs(a)
+        assert flips.sum() <= max(2, a.size // 500), f"{f}: {flips.sum()} of {a.size} printed sums differ"
