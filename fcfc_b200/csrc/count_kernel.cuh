@@ -651,7 +651,7 @@ __device__ __forceinline__ f32x2 mul2_uncontracted(f32x2 a, f32x2 b, float negze
 // buffer holds the 32 secondary points as 16 pairs, [pair][x0 x1 y0 y1 z0 z1 - -] (32 bytes per pair).  With two-word
 // entries ((s,mu), (s_perp,pi)) the packed results (d2_0, d2_1), (dz_0, dz_1) would have to be re-paired for the
 // 64-bit push: measured slower than the scalar loop (474 vs 460 ms on the bench workload; two 32-bit pushes: 467 ms).
-template <class T, int BIN, bool BOX, bool WT> struct PairLoop { static constexpr bool kPacked = sizeof(T) == 4 && BIN == BIN_ISO && !WT; };
+template <class T, int BIN, bool BOX, bool WT> struct PairLoop { static constexpr bool kPacked = sizeof(T) == 4 && (BOX || BIN == BIN_ISO) && !WT; };
 __device__ __forceinline__ unsigned staged_pair_addr(unsigned sbuf_s, int j) { return sbuf_s + (unsigned) (j >> 1) * 32u + (unsigned) (j & 1) * 4u; }
 
 // Tile point held by `lane` as its r-th primary (other assignments, e.g. reversed in odd r, measured no better).
@@ -678,32 +678,58 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
       f32x2 X, Y, Z;
       asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
       asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
+      float zz[2];
+      upk2(Z, zz[0], zz[1]);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const f32x2 dx = sub2(pk2(ax[r], ax[r]), X), dy = sub2(pk2(ay[r], ay[r]), Y), dz = sub2(pk2(az[r], az[r]), Z);
-        f32x2 d2, aux;
-        if (BIN == BIN_SPI) {                     // box (s_perp, pi): metric_common.c:157-165, 416-424
-          d2 = (ARITH == ARITH_SCALAR) ? add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)) : fma2(dy, dy, mul2(dx, dx));
-          aux = dz;
-        } else {
+        const f32x2 dx = sub2(pk2(ax[r], ax[r]), X), dy = sub2(pk2(ay[r], ay[r]), Y);
+        float d2h[2], auxh[2];
+        if (NW == 1) {                            // isotropic: everything packed, only d2 is kept
+          const f32x2 dz = sub2(pk2(az[r], az[r]), Z);
           const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
+          f32x2 d2;
           if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
           else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
           else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
-          aux = (BOX && BIN == BIN_SMU) ? dz : dz2;
+          upk2(d2, d2h[0], d2h[1]);
+          auxh[0] = auxh[1] = 0.0f;
+        } else {
+          // two-word entries (d2, aux) are pushed with one 64-bit store each: the last operation of the d2 chain and
+          // the z difference are scalar, so that d2_h and aux_h can be produced side by side in registers
+          float dzh[2], dyh[2];
+          dzh[0] = __fsub_rn(az[r], zz[0]); dzh[1] = __fsub_rn(az[r], zz[1]);
+          upk2(dy, dyh[0], dyh[1]);
+          if (BIN == BIN_SPI) {                   // box (s_perp, pi): metric_common.c:157-165, 416-424
+            float mxh[2], myh[2];
+            if (ARITH == ARITH_SCALAR) {
+              upk2(mul2_uncontracted(dx, dx, negzero), mxh[0], mxh[1]); upk2(mul2_uncontracted(dy, dy, negzero), myh[0], myh[1]);
+            } else upk2(mul2(dx, dx), mxh[0], mxh[1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(mxh[h], myh[h]) : __fmaf_rn(dyh[h], dyh[h], mxh[h]);
+              auxh[h] = fabsf(dzh[h]);
+            }
+          } else {                                // box (s, mu): :170-172 / :426-430
+            const float dz2h[2] = {__fmul_rn(dzh[0], dzh[0]), __fmul_rn(dzh[1], dzh[1])};
+            float uh[2];
+            if (ARITH == ARITH_SCALAR) upk2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), uh[0], uh[1]);
+            else upk2(fma2(dx, dx, pk2(dz2h[0], dz2h[1])), uh[0], uh[1]);
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+              d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(uh[h], dz2h[h]) : __fmaf_rn(dyh[h], dyh[h], uh[h]);
+              auxh[h] = dzh[h];
+            }
+          }
         }
-        float d2h[2], auxh[2];
-        upk2(d2, d2h[0], d2h[1]); upk2(aux, auxh[0], auxh[1]);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
-          if (BIN == BIN_SPI) auxh[h] = fabsf(auxh[h]);
           bool ok = d2h[h] < s2lim;
           if (BIN == BIN_SPI) ok = ok && (auxh[h] < P.pmax);
           if (GENERIC) ok = ok && (P.smin0 || d2h[h] >= P.s2min);
           if (GENERIC && BIN == BIN_SPI) ok = ok && (P.pmin0 || auxh[h] >= P.pmin);
           T e[NW];
           e[0] = d2h[h];
-          if (BIN != BIN_ISO) e[1 % NW] = auxh[h];
+          if (NW > 1) e[1 % NW] = auxh[h];
           Q.push(e, ok);
         }
       }
