@@ -668,13 +668,17 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
   constexpr bool kPacked = PairLoop<T, BIN, BOX, WT>::kPacked;
   const unsigned int sbuf_s = (unsigned int) __cvta_generic_to_shared(sbuf);
   if constexpr (kPacked && !SELF) {
-    // two secondary points per step: as many steps as cannot overflow the fullest queue even if every pair is accepted
-    const int steps = min((nj - j0 + 1) >> 1, (P.qdepth - 1 - ub) / (2 * R));
-    ub += steps * 2 * R;
+    // two secondary points per step.  Before every step one vote checks that each lane has room for 2 R more entries:
+    // the loop leaves only when a stack is really about to overflow (a worst-case bound on the pushes would
+    // leave every two or three steps at a 50 % acceptance rate).
+    constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+    const unsigned int lim = Q.base + (unsigned int) (P.qdepth - 1 - 2 * R) * S;      // proceed while fill + 2 R <= qdepth - 1
     unsigned int sa = sbuf_s + (unsigned int) (j0 >> 1) * 32u;     // j0 is even: this path always advances by pairs
-    const unsigned int se = sa + (unsigned int) steps * 32u;
+    const unsigned int sa0 = sa, se = sbuf_s + (unsigned int) ((nj + 1) >> 1) * 32u;
+    ub = P.qdepth;                // (no bound is tracked here: whoever needs one next measures the stacks first)
 #pragma unroll kEvalUnroll
     for (; sa != se; sa += 32u) {
+      if (__any_sync(0xffffffffu, Q.top > lim)) break;
       f32x2 X, Y, Z;
       asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
       asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
@@ -734,7 +738,7 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
         }
       }
     }
-    return min(j0 + 2 * steps, nj);
+    return min(j0 + (int) ((sa - sa0) >> 4), nj);
   }
   // as many points as cannot overflow the fullest queue even if every pair is accepted: no test inside the loop
   const int steps = min(nj - j0, (P.qdepth - 1 - ub) / R);
