@@ -740,16 +740,17 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
     }
     return min(j0 + (int) ((sa - sa0) >> 4), nj);
   }
-  // as many points as cannot overflow the fullest queue even if every pair is accepted: no test inside the loop
-  const int steps = min(nj - j0, (P.qdepth - 1 - ub) / R);
-  ub += steps * R;
-  const int jend = j0 + steps;
+  // one secondary point per step; as in the packed loop a vote before every step checks the real fill of the stacks
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  const unsigned int lim = Q.base + (unsigned int) (P.qdepth - 1 - R) * S;      // proceed while fill + R <= qdepth - 1
+  ub = P.qdepth;
   // the staged points are walked with a 32-bit shared-window address (one add per point, no index arithmetic)
   unsigned int sa = (unsigned int) __cvta_generic_to_shared(sbuf + j0);
-  const unsigned int se = sa + (unsigned int) steps * (unsigned int) sizeof(Vec4<T>);
+  const unsigned int se = (unsigned int) __cvta_generic_to_shared(sbuf + nj);
   int j = j0;
 #pragma unroll kEvalUnroll
   for (; sa != se; sa += (unsigned int) sizeof(Vec4<T>)) {
+    if (__any_sync(0xffffffffu, Q.top > lim)) break;
     Vec4<T> b;
     if constexpr (kPacked) {      // (only the tile against its own points gets here: SELF) pair layout, one point
       const unsigned int pa = staged_pair_addr(sbuf_s, j);
@@ -771,9 +772,8 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
       else { e[0] = aux; e[1 % NW] = as[r]; e[2 % NW] = b.s; e[3 % NW] = WT ? Ar<T>::mul(aw[r], bw) : (T) 0; }
       Q.push(e, ok);
     }
-    if (WT || SELF) j++;
+    j++;
   }
-  j = jend;
   return j;
 }
 
