@@ -114,6 +114,7 @@ template <class T> struct CountParams {
   int tabs_global;                      // lookup tables too large for shared memory: read them from global memory
   int hist_copies;                      // weighted shared-memory histogram: 32 lane-private copies (few bins) or 1
   int qdepth;                           // entries per lane of the accepted-pair queues (a multiple of 4)
+  int qkeep;                            // entries a drain leaves on the fullest stack
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
   unsigned long long *gevals;           // [0] candidate pair evaluations
@@ -932,7 +933,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
             } else j = (nr == 1) ? FCFC_CHUNK(1, false) : FCFC_CHUNK(RMAX, false);
             if (j >= nj) break;
             // a queue may overflow: the one place where queued pairs are binned
-            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, kPacked ? 2 * RMAX : RMAX, P.qdepth / 4);
+            ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, kPacked ? 2 * RMAX : RMAX, P.qkeep);
           }
 #undef FCFC_CHUNK
         }

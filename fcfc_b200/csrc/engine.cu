@@ -736,6 +736,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   P.qdepth = depth;
+  P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
+  if (const char *ek = getenv("FCFC_GPU_QKEEP")) P.qkeep = std::max(0, std::min(atoi(ek), depth / 2));       // experiment hook
   cudaEventRecord(ev1);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
