@@ -719,25 +719,27 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const bool fast_variant = !generic && !getenv("FCFC_GPU_FORCE_GENERIC") && (b->periodic || bintype == BIN_ISO);
   const bool tables_unused = fast_variant && P.stab_is_sqrt && ((bintype == BIN_SMU && P.mu_is_sqrt) || bintype == BIN_ISO);
   const bool force_ghist = getenv("FCFC_GPU_GLOBAL_HIST") != nullptr;       // experiment hook
+  // the packed pair loop (float, box or isotropic, unweighted: PairLoop::kPacked) takes 2 x 4 entries per step and
+  // needs that much room above what a drain leaves behind
+  const int dmin_variant = (is_float && (b->periodic || bintype == BIN_ISO) && !withwt) ? 12 : 8;
+  qdepth_max = std::max(qdepth_max, dmin_variant);
   for (auto &t : tries) {
     if (force_ghist && t.sh) continue;
     if (tables_unused && !t.tg && t.sh) continue;       // computed bins: deeper stacks beat resident tables
-    for (int d = qdepth_max; d >= t.dmin && !depth; d -= 4) {
+    for (int d = qdepth_max; d >= std::max(t.dmin, dmin_variant) && !depth; d -= 4) {
       pl = plan(t.sh, d, t.tg);
       if (pl.total + 1024 <= smem_max) { depth = d; v.smem_hist = t.sh; tabs_global = t.tg; }
     }
     if (depth) break;
   }
   if (!depth) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
-  // the packed pair loop (float, isotropic, unweighted: 4-byte entries) needs room for 2 x 4 entries above the
-  // quarter that a drain leaves behind
-  if (is_float && bintype == BIN_ISO && !withwt && depth < 12) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan leaves no room for the pair stacks"); return FCFC_GPU_ERR_CF; }
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   P.qdepth = depth;
   P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
   if (const char *ek = getenv("FCFC_GPU_QKEEP")) P.qkeep = std::max(0, std::min(atoi(ek), depth / 2));       // experiment hook
+  P.qkeep = std::max(0, std::min(P.qkeep, depth - 1 - (dmin_variant == 12 ? 8 : 4)));    // a drained stack must have room for the next step
   cudaEventRecord(ev1);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));

@@ -198,6 +198,27 @@ def test_tiny_reach_in_huge_volume(gpu, prec):
     assert_counts(got, want, True)
 
 
+@pytest.mark.parametrize("depth,keep", [(8, 0), (8, 4), (12, 1), (16, 8), (24, 3), (64, 0)])
+def test_stack_depth_and_keep(gpu, depth, keep, monkeypatch):
+    """The per-lane stacks at every depth the shared-memory plan can choose (shallow ones are what the weighted
+    double-precision variants get), with drains that leave nothing / half of the stack: same counts."""
+    monkeypatch.setenv("FCFC_GPU_QDEPTH", str(depth))
+    monkeypatch.setenv("FCFC_GPU_QKEEP", str(keep))
+    cat = box_catalog(6000, 250.0, 33)
+    for prec in ("float", "double"):
+        for kw, withwt in ((dict(bintype=1, smax=40.0, ds=1.0, nmu=30), False), (dict(bintype=0, smax=40.0, ds=2.0), False),
+                           (dict(bintype=2, smax=30.0, ds=1.0, pmin=0.0, pmax=40.0, dpi=2.0), True)):
+            c = cat if withwt else cat[:3]
+            got = gpu_counts(gpu, dict(box=250.0, **kw), True, prec, [c], ["DD"], withwt, arith=1)["DD"]
+            ob = oracle.setup(prec=prec[0], periodic=True, arith=1, box=250.0, **kw)
+            assert_counts(got, oracle.count(ob, oracle.preprocess(ob, c), withwt=withwt), withwt)
+    D, R = survey_catalog(3000, 34), survey_catalog(4000, 35)
+    kw = dict(bintype=1, smax=150.0, ds=5.0, nmu=20)
+    got = gpu_counts(gpu, kw, False, "double", [D, R], ["DR"], True)["DR"]
+    ob = oracle.setup(prec="d", periodic=False, **kw)
+    assert_counts(got, oracle.count(ob, oracle.preprocess(ob, D), oracle.preprocess(ob, R), withwt=True), True)
+
+
 def test_huge_histogram_uses_global_path(gpu):
     """ns = 600 x nmu = 255 = 153000 bins do not fit the shared-memory histogram: global-atomic variant."""
     kw = dict(box=500.0, bintype=1, smax=60.0, ds=0.1, nmu=255)
