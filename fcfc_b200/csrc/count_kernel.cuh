@@ -248,9 +248,11 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
       ok = d2 < s2lim;
     }
   } else {                                      // survey (s,mu) / (s_perp,pi): 2pt/metric_common.c:169-172, 341-357
+    // t = 2 (x1 . x2): the caller passes the primary already doubled (exact), which saves the final multiplication;
+    // every product and sum is then exactly twice the reference's, rounding included
     T t;
-    if (ARITH == ARITH_SCALAR) t = A::mul(A::add(A::add(A::mul(ax, b.x), A::mul(ay, b.y)), A::mul(az, b.z)), (T) 2);
-    else t = A::mul(A::fma(az, b.z, A::fma(ay, b.y, A::mul(ax, b.x))), (T) 2);
+    if (ARITH == ARITH_SCALAR) t = A::add(A::add(A::mul(ax, b.x), A::mul(ay, b.y)), A::mul(az, b.z));
+    else t = A::fma(az, b.z, A::fma(ay, b.y, A::mul(ax, b.x)));
     T s = A::add(as, b.s);
     d2 = A::sub(s, t);
     aux = t;
@@ -879,9 +881,10 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
       T ax[RMAX], ay[RMAX], az[RMAX];
 #pragma unroll
       for (int r = 0; r < RMAX; r++) {
-        ax[r] = BOX ? Ar<T>::add(px[r], sax) : px[r];
-        ay[r] = BOX ? Ar<T>::add(py[r], say) : py[r];
-        az[r] = BOX ? Ar<T>::add(pz[r], saz) : pz[r];
+        constexpr bool kDot = !BOX && BIN != BIN_ISO;     // survey (s,mu) / (s_perp,pi): dot-product form, see eval_pair
+        ax[r] = BOX ? Ar<T>::add(px[r], sax) : (kDot ? Ar<T>::add(px[r], px[r]) : px[r]);
+        ay[r] = BOX ? Ar<T>::add(py[r], say) : (kDot ? Ar<T>::add(py[r], py[r]) : py[r]);
+        az[r] = BOX ? Ar<T>::add(pz[r], saz) : (kDot ? Ar<T>::add(pz[r], pz[r]) : pz[r]);
       }
       while (b < e) {
         const int piece_end = min(e, b + kSegPieceMax);
