@@ -437,7 +437,7 @@ __device__ __forceinline__ float to_f32(double x) { return __double2float_rn(x);
 // (IMAD.HI shifts, IMAD product).  Returns the bin biased by bias_s + bias_m * ns, bias = 0x4B000000 >> k; the
 // caller folds the bias into the base address.  The biased bin of ANY pair that passed the range test lies in
 // [bias, bias + ntot + ns]: s <= ns (1 + 3e-7), nmu*mu <= nmu (1 + 4.5e-7).
-template <int BIN>
+template <int BIN, bool CLAMP = false>
 __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale, const float mscale_nmu,
                                          const unsigned int smask, const unsigned int mmask,
                                          const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, unsigned int &t) {
@@ -452,6 +452,7 @@ __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale,
     asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(e2), "l"(r2));
     asm("mov.b64 {%0, %1}, %2;" : "=f"(sr), "=f"(mr) : "l"(p2));
   } else sr = d2 * r;
+  if (CLAMP) mr = fminf(fabsf(mr), 1.000002f);  // survey: mu from separately rounded terms is not bounded by construction
   const unsigned int us = (unsigned int) __float_as_int(__fmaf_rz(sr, sscale, 8388609.0f));
   t = us & smask;
   int bin = (int) __umulhi(us, sshift_mul);     // us >> ks
@@ -466,6 +467,25 @@ __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale,
 __device__ __forceinline__ void red_shared_u32_add(unsigned a, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v));
 }
+
+// (d2, aux) of a queued pair as the floats fast_bins works on.  Box / isotropic entries hold them directly.
+// Survey (s,mu) entries hold (t, s1, s2[, w]) (2pt/metric_common.c:169-172): d2 = (s1 + s2) - t with the same two
+// operations as eval_pair, and the line-of-sight separation pi = |s1 - s2| / sqrt(s1 + s2 + t) plays the role of dz
+// (mu = pi / s).  Two more roundings and one more rsqrt.approx than the box form: the host widens the mu band.
+template <class T, int BIN, bool BOX, int NW>
+__device__ __forceinline__ void fast_inputs(const T (&e)[NW], float &d2f, float &auxf) {
+  if (BOX || BIN == BIN_ISO) { d2f = to_f32(e[0]); auxf = (BIN == BIN_SMU) ? to_f32(e[1 % NW]) : 0.0f; }
+  else {
+    using A = Ar<T>;
+    const T s = A::add(e[1 % NW], e[2 % NW]);
+    d2f = fmaxf(to_f32(A::sub(s, e[0])), 0.0f);         // (s - t can round below zero for coincident points)
+    const float df = to_f32(A::sub(e[1 % NW], e[2 % NW])), stf = to_f32(A::add(s, e[0]));
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(stf));
+    auxf = df * r;
+  }
+}
+template <int BIN, bool BOX, int NW> struct QWeight { static constexpr int kIndex = (BIN == BIN_ISO) ? 1 % NW : (BOX ? 2 % NW : 3 % NW); };
 
 // Exact re-binning of one flagged pair, out of line (a few pairs per ten thousand): keeps its registers and code
 // out of the drain loop.  Tables are read from global memory (P.stab / P.mutab), which is fine at this frequency.
@@ -484,7 +504,9 @@ __device__ __noinline__ void fix_entry(const CountParams<T> &P, unsigned int his
   else {
     const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
     unsigned int t;
-    const int fb = fast_bins<BIN>(to_f32(e[0]), (BIN == BIN_SMU) ? to_f32(e[1 % NW]) : 0.0f, P.fb_sscale, P.fb_mscale, P.fb_smask,
+    float d2f, auxf;
+    fast_inputs<T, BIN, BOX, NW>(e, d2f, auxf);
+    const int fb = fast_bins<BIN, !(BOX || BIN == BIN_ISO)>(d2f, auxf, P.fb_sscale, P.fb_mscale, P.fb_smask,
                                   P.fb_mmask, 1u << (32 - P.fb_sshift), 1u << (32 - P.fb_mshift), P.ns, t) - bias;
     if (b != fb) {
       red_shared_u32_add(hist_s + 4u * (unsigned int) fb, 0xffffffffu);
@@ -499,7 +521,7 @@ __device__ __noinline__ void fix_entry(const CountParams<T> &P, unsigned int his
 // unconditionally (FULL: all lanes still have entries; otherwise lanes that have run dry aim at a private dump
 // slot); weighted: predicated.  One bit per pair records whether it was clean (carry chain:
 // clean = 2 * clean + (t != 0), two instructions); the rare other pairs are re-binned exactly after the loop.
-template <class T, int BIN, bool WT, int NW, bool FULL>
+template <class T, int BIN, bool BOX, bool WT, int NW, bool FULL>
 __device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigned int hist_adj, const unsigned int HS, const unsigned int dump,
                                                 unsigned int &rp, int k0, int k1, int mine, unsigned int &clean) {
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
@@ -514,11 +536,12 @@ __device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigne
 #pragma unroll
     for (int i = 0; i < NE; i++) {
       unsigned int t;
-      const int bin = fast_bins<BIN>(to_f32(e[i][0]), (BIN == BIN_SMU) ? to_f32(e[i][1 % NW]) : 0.0f, sscale, mscale, smask,
-                                     mmask, smul, mmul, P.ns, t);
+      float d2f, auxf;
+      fast_inputs<T, BIN, BOX, NW>(e[i], d2f, auxf);
+      const int bin = fast_bins<BIN, !(BOX || BIN == BIN_ISO)>(d2f, auxf, sscale, mscale, smask, mmask, smul, mmul, P.ns, t);
       const bool h = FULL || (k + i < mine);
       unsigned int addr = hist_adj + HS * (unsigned int) bin;
-      if (WT) red_shared_f64(addr, (double) e[i][(BIN == BIN_ISO) ? 1 % NW : 2 % NW], h && t != 0u);
+      if (WT) red_shared_f64(addr, (double) e[i][QWeight<BIN, BOX, NW>::kIndex], h && t != 0u);
       else {
         if (!FULL) addr = h ? addr : dump;
         red_shared_u32_add(addr, 1u);
@@ -542,8 +565,8 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
   // rounds in which every lane still has four entries (one ragged loop for everything measured 1.5 % slower)
   const int nfull = __reduce_min_sync(0xffffffffu, mine) & ~3;
   unsigned int clean = 0;       // one bit per round, most recent round in bit 0
-  drain_fast_loop<T, BIN, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
-  drain_fast_loop<T, BIN, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
+  drain_fast_loop<T, BIN, BOX, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
+  drain_fast_loop<T, BIN, BOX, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
   unsigned int flagged = ~clean & (0xffffffffu >> (32 - rounds));
   while (flagged) {                                             // rare
     const int k = rounds - __ffs((int) flagged);
@@ -620,6 +643,8 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) {
     if (BIN != BIN_SPI && P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
     else drain_lut<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
+  } else if (!GENERIC && SMEMHIST && BIN == BIN_SMU && P.stab_is_sqrt && P.mu_is_sqrt) {
+    drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);       // survey (s,mu): computed bins too (fast_inputs)
   } else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
   return max(mx - rounds, 0);
 }
@@ -822,7 +847,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     *reinterpret_cast<float *>(smem + pl.off_misc + 4) = -0.0f;
   }
   // queues start zeroed: slots past a queue's tail are read (and ignored) by the two-entry drain
-  for (int i = threadIdx.x * 16; i < kWarpsPerBlock * pl.queue_per_warp; i += kThreads * 16)
+  for (int i = threadIdx.x * 16; i < pl.total - pl.off_queue; i += kThreads * 16)    // (including the over-read pad behind the last stack)
     *reinterpret_cast<uint4 *>(smem + pl.off_queue + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
   FastCtx F;

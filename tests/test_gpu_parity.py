@@ -198,6 +198,22 @@ def test_tiny_reach_in_huge_volume(gpu, prec):
     assert_counts(got, want, True)
 
 
+@pytest.mark.parametrize("prec", ["double", "float"])
+@pytest.mark.parametrize("arith", [0, 1])
+def test_medium_survey_smu_vs_oracle(gpu, prec, arith):
+    """Survey (s,mu) with computed bins (pi / s from reciprocal square roots, flagged pairs re-binned exactly):
+    10^8 - 10^9 candidate pairs against the brute-force oracle, unweighted exact, weighted to 1e-12."""
+    D, R = survey_catalog(16000, 51), survey_catalog(24000, 52)
+    kw = dict(bintype=1, smax=120.0, ds=4.0, nmu=60)
+    ob = oracle.setup(prec=prec[0], periodic=False, arith=arith, **kw)
+    pD, pR = oracle.preprocess(ob, D), oracle.preprocess(ob, R)
+    got = gpu_counts(gpu, kw, False, prec, [D[:3], R[:3]], ["DD", "DR"], False, arith)
+    np.testing.assert_array_equal(got["DD"], oracle.count(ob, oracle.preprocess(ob, D[:3])))
+    np.testing.assert_array_equal(got["DR"], oracle.count(ob, oracle.preprocess(ob, D[:3]), oracle.preprocess(ob, R[:3])))
+    gotw = gpu_counts(gpu, kw, False, prec, [D, R], ["DR"], True, arith)["DR"]
+    assert_counts(gotw, oracle.count(ob, pD, pR, withwt=True), True)
+
+
 @pytest.mark.parametrize("depth,keep", [(8, 0), (8, 4), (12, 1), (16, 8), (24, 3), (64, 0)])
 def test_stack_depth_and_keep(gpu, depth, keep, monkeypatch):
     """The per-lane stacks at every depth the shared-memory plan can choose (shallow ones are what the weighted
