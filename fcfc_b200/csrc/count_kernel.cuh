@@ -101,6 +101,7 @@ template <class T> struct CountParams {
   // neighbour stencil: rows (dx, dy, dz_lo, dz_hi)
   const int4 *rows; int nrows;
   // binning
+  T s2max_pre;                          // survey (s_perp,pi): padded s2max of the division-free pre-test (eval_pair)
   T s2min, s2max, pmin, pmax, premax, pmax_pre, nmu2f;
   int ns, np, nmu2, ntot, soff, poff;
   int tab_hybrid, swidth, pwidth, with_mu_one, smin0, pmin0;
@@ -261,8 +262,11 @@ __device__ __forceinline__ bool eval_pair(const CountParams<T> &P, T ax, T ay, T
       // cheap necessary condition for pi^2 = d*d / (s + t) < p2max, without the division (the exact test is
       // repeated in finish_pair): d*d < (s + t) * p2max * (1 + 8 eps).  Cuts the queue traffic of survey
       // (s_perp, pi) counts, whose accepted region is a thin cylinder inside the searched sphere.
-      const T d = A::sub(as, b.s);
-      ok = ok && (A::mul(d, d) < A::mul(A::add(s, t), P.pmax_pre));
+      const T d = A::sub(as, b.s), dd = A::mul(d, d), st = A::add(s, t);
+      ok = ok && (dd < A::mul(st, P.pmax_pre));
+      // and for s_perp^2 = s^2 - pi^2 < s2max, again without the division: (s^2 - s2max') (s + t) < d*d, with s2max'
+      // padded by the host for every rounding on the way.  Three quarters of the sphere-shaped candidates fail it.
+      ok = ok && (A::mul(A::sub(d2, P.s2max_pre), st) < dd);
     }
   }
   if (GENERIC && BIN != BIN_SPI) ok = ok && (P.smin0 || d2 >= P.s2min);

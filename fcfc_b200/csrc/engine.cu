@@ -648,6 +648,11 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     P.premax = (T) pm; if ((double) P.premax < pm) P.premax = std::nextafter(P.premax, (T) INFINITY);
     const double pp = pmax * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
     P.pmax_pre = (T) pp; if ((double) P.pmax_pre < pp) P.pmax_pre = std::nextafter(P.pmax_pre, (T) INFINITY);
+    // s_perp^2 pre-test (s^2 - c)(s + t) < d*d: c >= s2max (1 + 2 eps) + 3.2 eps max(s^2) keeps it a necessary
+    // condition of the exact test through every rounding (derivation in DESIGN.md); padded tenfold
+    const double eps = is_float ? (double) FLT_EPSILON : DBL_EPSILON;
+    const double sp = s2max * (1 + 32 * eps) + 32 * eps * pm;
+    P.s2max_pre = (T) sp; if ((double) P.s2max_pre < sp) P.s2max_pre = std::nextafter(P.s2max_pre, (T) INFINITY);
   }
   P.nmu2 = nmu * nmu; P.nmu2f = (T) (nmu * nmu);
   P.ns = ns; P.np = np; P.ntot = (int) ntot;
