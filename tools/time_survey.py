@@ -11,8 +11,11 @@ prec = sys.argv[3] if len(sys.argv) > 3 else "double"
 withref = len(sys.argv) > 4
 F.init()
 D, R = survey_catalog(nd, 1), survey_catalog(nr, 2)
+only = [int(v) for v in os.environ.get("FCFC_TS_BINTYPES", "2,1,0").split(",")]      # restrict the binning schemes (large catalogues)
 for bt, kw in ((2, dict(smax=40., ds=2., pmin=0., pmax=80., dpi=1.)), (1, dict(smax=200., ds=5., nmu=120)), (0, dict(smax=200., ds=5.))):
-    for wt in (True, False):
+    if bt not in only:
+        continue
+    for wt in ((True,) if os.environ.get("FCFC_TS_WEIGHTED_ONLY") else (True, False)):
         b = F.Bins(periodic=False, prec=prec, bintype=bt, arith=0, **kw)
         gd = F.Catalog(*(D if wt else D[:3]), bins=b); gr = F.Catalog(*(R if wt else R[:3]), bins=b)
         out = []
