@@ -37,6 +37,9 @@ WORKLOADS = {
     # name: (N, L, bintype, nmu)  -- s in [0,200) step 5 everywhere
     "c2_box_smu_1e7": dict(n=10_000_000, box=2000.0, bintype=1, nmu=120, desc="FCFC_2PT_BOX xi(s,mu) 10^7 pts L=2000 40x120 bins DD"),
     "c1_box_iso_1e6": dict(n=1_000_000, box=1000.0, bintype=0, nmu=1, desc="FCFC_2PT_BOX xi(s) 10^6 pts L=1000 40 bins DD"),
+    # single-GPU version of configs[3] (clustered mock): Neyman-Scott blobs + 20 % background
+    "c4_box_smu_clustered_1e7": dict(n=10_000_000, box=2000.0, bintype=1, nmu=120, clustered=True,
+                                     desc="FCFC_2PT_BOX xi(s,mu) 10^7 clustered pts (Neyman-Scott, sigma=1.5, 20% background) L=2000 40x120 bins DD"),
 }
 METRIC = "pair_evals_per_sec"
 UNIT = "pair evaluations/s"
@@ -46,6 +49,22 @@ KAPPA_FILE = os.path.join(ROOT, "profiles", "workload_kappa.json")
 def make_box(n, L, seed=20261017):
     rng = np.random.default_rng(seed)
     return [np.ascontiguousarray(rng.random(n) * L) for _ in range(3)]
+
+
+def make_clustered_box(n, L, seed=20261017, sigma=1.5, frac_bg=0.2):
+    """Neyman-Scott style mock: n/50 parents, 40 Gaussian children each, 20 % uniform background."""
+    rng = np.random.default_rng(seed)
+    nbg = int(n * frac_bg)
+    ncl = n - nbg
+    par = rng.random((max(1, ncl // 40), 3)) * L
+    x = np.concatenate([par[rng.integers(0, len(par), ncl)] + rng.normal(0, sigma, (ncl, 3)), rng.random((nbg, 3)) * L]) % L
+    x[x >= L] = 0.0
+    rng.shuffle(x)
+    return [np.ascontiguousarray(x[:, k]) for k in range(3)]
+
+
+def make_catalog(wl, n, L, seed=20261017):
+    return make_clustered_box(n, L, seed) if wl.get("clustered") else make_box(n, L, seed)
 
 
 class ClockSampler:
@@ -100,7 +119,7 @@ def run_reference_arm(args, wl, sample_n, prec):
     from oracle import refdrv
     dens = wl["n"] / wl["box"] ** 3
     Ls = (sample_n / dens) ** (1.0 / 3.0)
-    cat = make_box(sample_n, Ls, seed=7)
+    cat = make_catalog(wl, sample_n, Ls, seed=7)
     flav = refdrv.best_simd_flavour("flt" if prec == "float" else "dbl")
     p, isa = flav.split("_")
     kw = dict(bintype=wl["bintype"], smin=0.0, smax=200.0, ds=5.0)
@@ -123,7 +142,7 @@ def run_reference_arm(args, wl, sample_n, prec):
     except Exception:
         pass
     return dict(seconds=t, pairs=pairs, value=kappa * pairs / t, kappa=kappa, cores=cores, flavour=flav,
-                sample=f"{sample_n} uniform points in a {Ls:.1f} Mpc/h box (same density and bins as the workload), "
+                sample=f"{sample_n} {'clustered' if wl.get('clustered') else 'uniform'} points in a {Ls:.1f} Mpc/h box (same density and bins as the workload), "
                        f"count_pairs only, reference build {flav}, OMP_NUM_THREADS={cores}, in-range pairs={pairs}, "
                        f"{t:.3f} s; value = evals_per_inrange_pair({kappa:.3f}) x pairs / s")
 
@@ -183,7 +202,7 @@ def main():
     bins = F.Bins(periodic=True, prec=args.prec, arith=args.arith, box=wl["box"], bintype=wl["bintype"], smin=0.0, smax=200.0,
                   ds=5.0, nmu=wl["nmu"])
     npdt = np.float32 if args.prec == "float" else np.float64
-    xyz = make_box(wl["n"], wl["box"])
+    xyz = make_catalog(wl, wl["n"], wl["box"])
     # pinned host buffers of the build's `real` type (what the FCFC host holds after reading the catalogue)
     pinned = [torch.from_numpy(a.astype(npdt)).pin_memory() for a in xyz]
     host = [p.numpy() for p in pinned]

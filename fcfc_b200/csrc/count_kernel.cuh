@@ -48,15 +48,6 @@ constexpr int kMaxRows = 1024;          // stencil rows kept in shared memory
 #endif
 constexpr int kEvalUnroll = FCFC_EVAL_UNROLL;   // secondary points per iteration of the pair loop
 constexpr int kSegPieceMax = 1 << 19;   // secondary points per overflow-accounting piece
-// How the fast drain of unweighted counts records the pairs that must be re-binned exactly (see drain_fast_loop):
-//   0  one "clean" bit per pair: product of the masked fraction bits on a carry chain (5 instructions per pair)
-//   1  one bit per group of four pairs: masked fraction bits folded with a three-input minimum
-//   2  one bit per group of four pairs: the fraction bits are the low half of the 32 x 32 -> 64-bit product whose
-//      high half is the bin (IMAD.WIDE), folded with a three-input minimum (1.5 instructions per pair)
-#ifndef FCFC_FLAG_MODE
-#define FCFC_FLAG_MODE 0
-#endif
-constexpr int kFlagMode = FCFC_FLAG_MODE;
 
 template <class T> struct Vec4;
 template <> struct __align__(16) Vec4<float> { float x, y, z, s; };
@@ -477,47 +468,6 @@ __device__ __forceinline__ int fast_bins(float d2, float dz, const float sscale,
   return bin;
 }
 
-// The same bins for the group-flag drains (kFlagMode 1, 2): instead of a per-pair flag the fraction bits of s and
-// nmu*mu are folded into `acc` with a three-input minimum (VIMNMX3); a group of pairs is clean iff acc stays at or
-// above the band.  Mode 1 folds the masked fraction bits (band: acc == 0).  Mode 2 takes the bin and the fraction
-// bits from one widening multiplication by 2^(32-k): the high word is us >> k, the low word holds the k fraction
-// bits left-aligned, and (fraction + 1) in {0..3} (s) / {0, 1} (mu) become low words below 2^(34-ks) = 2^(33-km);
-// the host picks km = ks - 1 for this mode so that one threshold serves both.
-template <int BIN, bool CLAMP = false>
-__device__ __forceinline__ int fast_bins_acc(float d2, float dz, const float sscale, const float mscale_nmu,
-                                             const unsigned int smask, const unsigned int mmask,
-                                             const unsigned int sshift_mul, const unsigned int mshift_mul, int ns, unsigned int &acc) {
-  float r;
-  asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(d2 + 1e-30f));
-  float sr, mr = 0.0f;
-  if (BIN == BIN_SMU) {
-    unsigned long long e2, r2, p2;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(e2) : "f"(d2), "f"(dz));
-    asm("mov.b64 %0, {%1, %1};" : "=l"(r2) : "f"(r));
-    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(p2) : "l"(e2), "l"(r2));
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(sr), "=f"(mr) : "l"(p2));
-  } else sr = d2 * r;
-  if (CLAMP) mr = fminf(fabsf(mr), 1.000002f);
-  const unsigned int us = (unsigned int) __float_as_int(__fmaf_rz(sr, sscale, 8388609.0f));
-  int bin;
-  unsigned int fs, fm = 0xffffffffu;
-  if (kFlagMode == 2) {
-    unsigned int hi;
-    asm("{.reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p;}" : "=r"(fs), "=r"(hi) : "r"(us), "r"(sshift_mul));   // IMAD.WIDE (fma pipe), not two shifts
-    bin = (int) hi;
-  } else { bin = (int) __umulhi(us, sshift_mul); fs = us & smask; }
-  if (BIN == BIN_SMU) {
-    const unsigned int um = (unsigned int) __float_as_int(__fmaf_rz(fabsf(mr), mscale_nmu, 8388609.0f));
-    if (kFlagMode == 2) {
-      unsigned int hi;
-      asm("{.reg .u64 p; mul.wide.u32 p, %2, %3; mov.b64 {%0, %1}, p;}" : "=r"(fm), "=r"(hi) : "r"(um), "r"(mshift_mul));
-      bin += (int) hi * ns;
-    } else { bin += (int) __umulhi(um, mshift_mul) * ns; fm = um & mmask; }
-    acc = min(min(acc, fs), fm);
-  } else acc = min(acc, fs);
-  return bin;
-}
-
 __device__ __forceinline__ void red_shared_u32_add(unsigned a, unsigned v) {
   asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v));
 }
@@ -553,18 +503,15 @@ __device__ __noinline__ void fix_entry(const CountParams<T> &P, unsigned int his
   G.stab = P.stab; G.ptab = P.ptab; G.mutab = P.mutab; G.s2bin = P.s2bin; G.pbin = P.pbin;
   T e[NW], w;
   QOps<T, NW>::load(qaddr, e);
-  if (WT) {
-    const int b = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
-    if (b >= 0) red_shared_f64(hist_s + hlane + hstride * (unsigned int) b, (double) w, true);
-  } else {
+  const int b = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
+  if (WT) { if (b >= 0) red_shared_f64(hist_s + hlane + hstride * (unsigned int) b, (double) w, true); }
+  else {
     const int bias = (int) (0x4B000000u >> P.fb_sshift) + ((BIN == BIN_SMU) ? (int) (0x4B000000u >> P.fb_mshift) * P.ns : 0);
     unsigned int t;
     float d2f, auxf;
     fast_inputs<T, BIN, BOX, NW>(e, d2f, auxf);
     const int fb = fast_bins<BIN, !(BOX || BIN == BIN_ISO)>(d2f, auxf, P.fb_sscale, P.fb_mscale, P.fb_smask,
                                   P.fb_mmask, 1u << (32 - P.fb_sshift), 1u << (32 - P.fb_mshift), P.ns, t) - bias;
-    if (kFlagMode != 0 && t != 0u) return;      // group flags: the clean members of a flagged group need nothing
-    const int b = bin_entry<T, BIN, BOX, WT, ARITH, false, NW>(P, G, e, w);
     if (b != fb) {
       red_shared_u32_add(hist_s + 4u * (unsigned int) fb, 0xffffffffu);
       if (b >= 0) red_shared_u32_add(hist_s + 4u * (unsigned int) b, 1u);
@@ -585,28 +532,11 @@ __device__ __forceinline__ void drain_fast_loop(const CountParams<T> &P, unsigne
   constexpr int NE = 4;
   const float sscale = P.fb_sscale, mscale = P.fb_mscale;
   const unsigned int smask = P.fb_smask, mmask = P.fb_mmask, smul = 1u << (32 - P.fb_sshift), mmul = 1u << (32 - P.fb_mshift);
-  const unsigned int negband = (kFlagMode == 2) ? 0u - (1u << (34 - P.fb_sshift)) : 0xffffffffu;
 #pragma unroll 1
   for (int k = k0; k < k1; k += NE, rp += NE * S) {
     T e[NE][NW];
 #pragma unroll
     for (int i = 0; i < NE; i++) QOps<T, NW>::load(rp + i * S, e[i]);   // slots above the old top hold stale entries: ignored
-    if constexpr (!WT && kFlagMode != 0) {
-      // group flags: one clean bit per iteration (four pairs); fix_entry sorts out which member raised it
-      unsigned int acc = 0xffffffffu;
-#pragma unroll
-      for (int i = 0; i < NE; i++) {
-        float d2f, auxf;
-        fast_inputs<T, BIN, BOX, NW>(e[i], d2f, auxf);
-        const int bin = fast_bins_acc<BIN, !(BOX || BIN == BIN_ISO)>(d2f, auxf, sscale, mscale, smask, mmask, smul, mmul, P.ns, acc);
-        unsigned int addr = hist_adj + HS * (unsigned int) bin;
-        if (!FULL) addr = (k + i < mine) ? addr : dump;
-        red_shared_u32_add(addr, 1u);
-      }
-      // clean = 2 * clean + (acc >= band): the carry of acc + (2^32 - band); band = 1 for the masked bits of mode 1
-      asm("{.reg .u32 tmp; add.cc.u32 tmp, %1, %2; addc.u32 %0, %0, %0;}" : "+r"(clean) : "r"(acc), "r"(negband));
-      continue;
-    }
 #pragma unroll
     for (int i = 0; i < NE; i++) {
       unsigned int t;
@@ -641,19 +571,6 @@ __device__ __forceinline__ void drain_fast(const CountParams<T> &P, const BlockC
   unsigned int clean = 0;       // one bit per round, most recent round in bit 0
   drain_fast_loop<T, BIN, BOX, WT, NW, true>(P, hist_adj, hs, dump, rp, 0, nfull, mine, clean);
   drain_fast_loop<T, BIN, BOX, WT, NW, false>(P, hist_adj, hs, dump, rp, nfull, rounds, mine, clean);
-  if constexpr (!WT && kFlagMode != 0) {
-    const int ng = rounds >> 2;                                 // one bit per group of four rounds, most recent group in bit 0
-    unsigned int flagged = ~clean & (0xffffffffu >> (32 - ng));
-    while (flagged) {                                           // rare
-      const int k4 = 4 * (ng - __ffs((int) flagged));
-      flagged &= flagged - 1;
-#pragma unroll 1
-      for (int k = k4; k < min(k4 + 4, mine); k++)
-        fix_entry<T, BIN, BOX, WT, ARITH, NW>(P, F.hist_s, F.hstride, F.hlane, Q.top + (unsigned int) k * S);
-    }
-    __syncwarp();
-    return;
-  }
   unsigned int flagged = ~clean & (0xffffffffu >> (32 - rounds));
   while (flagged) {                                             // rare
     const int k = rounds - __ffs((int) flagged);

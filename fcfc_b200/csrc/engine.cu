@@ -698,10 +698,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     // budget with a factor >= 2 to spare, and bin * 2^k must stay below 2^23
     auto pick = [](double need, int nbin) { int k = 20; while (k > 4 && (std::ldexp(1.0, -k) < need || (double) (nbin + 2) * std::ldexp(1.0, k) >= 8388608.0)) k--; return k; };
     // (survey (s,mu): mu comes from two approximate reciprocal square roots and three converted terms, 9.5e-7 relative)
-    int ks = pick(2.5 * 3e-7 * (ns + 1), ns), km = pick(2.2 * (b->periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
-    // kFlagMode 2 compares the left-aligned fraction bits of s and nmu*mu with one threshold: km = ks - 1 (fast_bins_acc);
-    // a smaller k only widens the band
-    if (kFlagMode == 2 && bintype == BIN_SMU) { ks = std::min(ks, km + 1); km = ks - 1; }
+    const int ks = pick(2.5 * 3e-7 * (ns + 1), ns), km = pick(2.2 * (b->periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
     P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
     P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
     if (ks < 6 || km < 6) P.stab_is_sqrt = 0;   // too many bins for the fixed-point trick: use the exact path
