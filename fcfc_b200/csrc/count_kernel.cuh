@@ -48,6 +48,9 @@ constexpr int kMaxRows = 1024;          // stencil rows kept in shared memory
 #endif
 constexpr int kEvalUnroll = FCFC_EVAL_UNROLL;   // secondary points per iteration of the pair loop
 constexpr int kSegPieceMax = 1 << 19;   // secondary points per overflow-accounting piece
+#ifndef FCFC_DENSE
+#define FCFC_DENSE 1                    // 0 compiles the dense-cell path out (experiments)
+#endif
 
 template <class T> struct Vec4;
 template <> struct __align__(16) Vec4<float> { float x, y, z, s; };
@@ -100,6 +103,9 @@ template <class T> struct CountParams {
   T bsize[3];
   // neighbour stencil: rows (dx, dy, dz_lo, dz_hi)
   const int4 *rows; int nrows;
+  // per row: the sub-range (dz_lo, dz_hi) of its cells that lie entirely within the maximum separation of every point of
+  // the tile's cell ("dense" cells: every pair is in range, see do_chunk_dense); null when the dense path is not used
+  const int2 *rows_in;
   // binning
   T s2max_pre;                          // survey (s_perp,pi): padded s2max of the division-free pre-test (eval_pair)
   T s2min, s2max, pmin, pmax, premax, pmax_pre, nmu2f;
@@ -108,6 +114,7 @@ template <class T> struct CountParams {
   int mu_is_sqrt, stab_is_sqrt, ptab_is_ident;     // tables that equal floor(sqrt(i)) / i are computed, not looked up
   // fast-bin fixed-point scales: s and nmu*mu are truncated after multiplication by 2^ks / 2^km (see fast_bins)
   float fb_sscale, fb_mscale; unsigned int fb_smask, fb_mmask, fb_sshift, fb_mshift;
+  unsigned int fb_smul, fb_mmul, fb_bias;        // 2^(32 - shift) (shifts as IMAD.HI) and the bias of the fast bins, (0x4B000000 >> ks) + (0x4B000000 >> km) * ns
   const uint8_t *stab; const uint8_t *ptab; const uint8_t *mutab;
   int nstab, nptab;                     // entries
   const T *s2bin; const T *pbin;
@@ -679,6 +686,51 @@ __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm(
 // rounded product and leaves nothing to contract.
 __device__ __forceinline__ f32x2 mul2_uncontracted(f32x2 a, f32x2 b, float negzero) { return fma2(a, b, pk2(negzero, negzero)); }
 
+// Squared separations (and the second queue word) of one primary against the two secondary points of a staged pair,
+// on packed f32x2 arithmetic: bit-identical to the scalar sequences of eval_pair.
+template <int BIN, bool BOX, int ARITH, int NW>
+__device__ __forceinline__ void packed_dist(const float axr, const float ayr, const float azr, const f32x2 X, const f32x2 Y, const f32x2 Z,
+                                            const float (&zz)[2], const float negzero, float (&d2h)[2], float (&auxh)[2]) {
+    const f32x2 dx = sub2(pk2(axr, axr), X), dy = sub2(pk2(ayr, ayr), Y);
+    if (NW == 1) {                            // isotropic: everything packed, only d2 is kept
+      const f32x2 dz = sub2(pk2(azr, azr), Z);
+      const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
+      f32x2 d2;
+      if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
+      else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
+      else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
+      upk2(d2, d2h[0], d2h[1]);
+      auxh[0] = auxh[1] = 0.0f;
+    } else {
+      // two-word entries (d2, aux) are pushed with one 64-bit store each: the last operation of the d2 chain and
+      // the z difference are scalar, so that d2_h and aux_h can be produced side by side in registers
+      float dzh[2], dyh[2];
+      dzh[0] = __fsub_rn(azr, zz[0]); dzh[1] = __fsub_rn(azr, zz[1]);
+      upk2(dy, dyh[0], dyh[1]);
+      if (BIN == BIN_SPI) {                   // box (s_perp, pi): metric_common.c:157-165, 416-424
+        float mxh[2], myh[2];
+        if (ARITH == ARITH_SCALAR) {
+          upk2(mul2_uncontracted(dx, dx, negzero), mxh[0], mxh[1]); upk2(mul2_uncontracted(dy, dy, negzero), myh[0], myh[1]);
+        } else upk2(mul2(dx, dx), mxh[0], mxh[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(mxh[h], myh[h]) : __fmaf_rn(dyh[h], dyh[h], mxh[h]);
+          auxh[h] = fabsf(dzh[h]);
+        }
+      } else {                                // box (s, mu): :170-172 / :426-430
+        const float dz2h[2] = {__fmul_rn(dzh[0], dzh[0]), __fmul_rn(dzh[1], dzh[1])};
+        float uh[2];
+        if (ARITH == ARITH_SCALAR) upk2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), uh[0], uh[1]);
+        else upk2(fma2(dx, dx, pk2(dz2h[0], dz2h[1])), uh[0], uh[1]);
+#pragma unroll
+        for (int h = 0; h < 2; h++) {
+          d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(uh[h], dz2h[h]) : __fmaf_rn(dyh[h], dyh[h], uh[h]);
+          auxh[h] = dzh[h];
+        }
+      }
+    }
+}
+
 // Variants whose pair loop runs packed: float, isotropic bins, unweighted (one word per queue entry).  Their staging
 // buffer holds the 32 secondary points as 16 pairs, [pair][x0 x1 y0 y1 z0 z1 - -] (32 bytes per pair).  With two-word
 // entries ((s,mu), (s_perp,pi)) the packed results (d2_0, d2_1), (dz_0, dz_1) would have to be re-paired for the
@@ -688,6 +740,63 @@ __device__ __forceinline__ unsigned staged_pair_addr(unsigned sbuf_s, int j) { r
 
 // Tile point held by `lane` as its r-th primary (other assignments, e.g. reversed in odd r, measured no better).
 __device__ __forceinline__ int tile_slot(int r, int lane) { return r * 32 + lane; }
+
+// "Dense" cells: every point of the secondary cell is within the maximum separation of every point of the tile's cell
+// (the host marks them per stencil row: CountParams::rows_in), so every pair is accepted -- a third of the accepted
+// pairs of the bench workload.  Such chunks skip the stacks: the pair loop computes the fast bins in place, with all
+// lanes busy, and increments the histogram directly (no push, no pop: 4 of the 7.5 shared-memory wavefronts an accepted
+// pair costs otherwise).  Pairs within the error band of a bin edge (fast_bins: t == 0) are pushed on the stack
+// instead, and the ordinary drain re-bins them exactly.  The range test is kept (one compare): exactness never depends
+// on the host's classification of the cells.  Only for the variants whose drain computes its bins (drain_fast).
+template <class T, int BIN, bool BOX, int ARITH, int R, int NW, int RMAX>
+__device__ __forceinline__ int do_chunk_dense(const CountParams<T> &P, LaneQueue<T, NW> &Q, int &ub, const unsigned int hist_s, const int lane,
+                                              const Vec4<T> *sbuf, int j0, int nj,
+                                              const T (&ax)[RMAX], const T (&ay)[RMAX], const T (&az)[RMAX],
+                                              const T s2lim, const float negzero) {
+  static_assert(sizeof(T) == 4, "the dense path runs on the packed float pair loop");
+  constexpr unsigned int S = LaneQueue<T, NW>::kStride;
+  const unsigned int sbuf_s = (unsigned int) __cvta_generic_to_shared(sbuf);
+  const unsigned int lim = Q.base + (unsigned int) (P.qdepth - 1 - 2 * R) * S;        // room for 2 R flagged pairs
+  unsigned int sa = sbuf_s + (unsigned int) (j0 >> 1) * 32u;
+  const unsigned int sa0 = sa, se = sbuf_s + (unsigned int) ((nj + 1) >> 1) * 32u;
+  const float sscale = P.fb_sscale, mscale = P.fb_mscale;
+  const unsigned int smask = P.fb_smask, mmask = P.fb_mmask, smul = P.fb_smul, mmul = P.fb_mmul;
+  const unsigned int hist_adj = hist_s - 4u * P.fb_bias;                  // base address of the biased fast bins (as in drain_fast)
+  const unsigned int dump = hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (unsigned int) lane;
+  ub = P.qdepth;
+#pragma unroll 1
+  for (; sa != se; sa += 32u) {
+    if (__any_sync(0xffffffffu, Q.top > lim)) break;
+    f32x2 X, Y, Z;
+    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
+    asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
+    float zz[2];
+    upk2(Z, zz[0], zz[1]);
+#pragma unroll
+    for (int r = 0; r < R; r++) {
+      float d2h[2], auxh[2];
+      packed_dist<BIN, BOX, ARITH, NW>(ax[r], ay[r], az[r], X, Y, Z, zz, negzero, d2h, auxh);
+#pragma unroll
+      for (int h = 0; h < 2; h++) {
+        unsigned int t, addr;
+        const int bin = fast_bins<BIN, false>(d2h[h], auxh[h], sscale, mscale, smask, mmask, smul, mmul, P.ns, t);
+        // in range (padding lanes and parked points are not; their bins are never used) and clean: counted here;
+        // in range and flagged: pushed.  ATOMS.POPC.INC cannot be predicated without a branch: everything that is
+        // not counted aims at the lane's dump slot.  One predicate chain, six instructions.
+        if (NW == 1)
+          asm volatile("{.reg .pred pk, pc, pf; setp.lt.f32 pk, %2, %3; setp.ne.and.u32 pc, %4, 0, pk; setp.eq.and.u32 pf, %4, 0, pk; "
+                       "selp.u32 %0, %5, %6, pc; @pf st.shared.f32 [%1], %2; @pf add.u32 %1, %1, %7;}"
+                       : "=r"(addr), "+r"(Q.top) : "f"(d2h[h]), "f"(s2lim), "r"(t), "r"(hist_adj + 4u * (unsigned int) bin), "r"(dump), "n"(S));
+        else
+          asm volatile("{.reg .pred pk, pc, pf; setp.lt.f32 pk, %2, %3; setp.ne.and.u32 pc, %4, 0, pk; setp.eq.and.u32 pf, %4, 0, pk; "
+                       "selp.u32 %0, %5, %6, pc; @pf st.shared.v2.f32 [%1], {%2, %8}; @pf add.u32 %1, %1, %7;}"
+                       : "=r"(addr), "+r"(Q.top) : "f"(d2h[h]), "f"(s2lim), "r"(t), "r"(hist_adj + 4u * (unsigned int) bin), "r"(dump), "n"(S), "f"(auxh[h]));
+        red_shared_u32_add(addr, 1u);
+      }
+    }
+  }
+  return min(j0 + (int) ((sa - sa0) >> 4), nj);
+}
 
 // One chunk of <= 32 staged secondary points against the R register-resident primaries of each lane,
 // starting at staged point j0.  Returns nj when the chunk is done, or the index of the point at which
@@ -718,45 +827,8 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
       upk2(Z, zz[0], zz[1]);
 #pragma unroll
       for (int r = 0; r < R; r++) {
-        const f32x2 dx = sub2(pk2(ax[r], ax[r]), X), dy = sub2(pk2(ay[r], ay[r]), Y);
         float d2h[2], auxh[2];
-        if (NW == 1) {                            // isotropic: everything packed, only d2 is kept
-          const f32x2 dz = sub2(pk2(az[r], az[r]), Z);
-          const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
-          f32x2 d2;
-          if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
-          else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
-          else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
-          upk2(d2, d2h[0], d2h[1]);
-          auxh[0] = auxh[1] = 0.0f;
-        } else {
-          // two-word entries (d2, aux) are pushed with one 64-bit store each: the last operation of the d2 chain and
-          // the z difference are scalar, so that d2_h and aux_h can be produced side by side in registers
-          float dzh[2], dyh[2];
-          dzh[0] = __fsub_rn(az[r], zz[0]); dzh[1] = __fsub_rn(az[r], zz[1]);
-          upk2(dy, dyh[0], dyh[1]);
-          if (BIN == BIN_SPI) {                   // box (s_perp, pi): metric_common.c:157-165, 416-424
-            float mxh[2], myh[2];
-            if (ARITH == ARITH_SCALAR) {
-              upk2(mul2_uncontracted(dx, dx, negzero), mxh[0], mxh[1]); upk2(mul2_uncontracted(dy, dy, negzero), myh[0], myh[1]);
-            } else upk2(mul2(dx, dx), mxh[0], mxh[1]);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(mxh[h], myh[h]) : __fmaf_rn(dyh[h], dyh[h], mxh[h]);
-              auxh[h] = fabsf(dzh[h]);
-            }
-          } else {                                // box (s, mu): :170-172 / :426-430
-            const float dz2h[2] = {__fmul_rn(dzh[0], dzh[0]), __fmul_rn(dzh[1], dzh[1])};
-            float uh[2];
-            if (ARITH == ARITH_SCALAR) upk2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), uh[0], uh[1]);
-            else upk2(fma2(dx, dx, pk2(dz2h[0], dz2h[1])), uh[0], uh[1]);
-#pragma unroll
-            for (int h = 0; h < 2; h++) {
-              d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(uh[h], dz2h[h]) : __fmaf_rn(dyh[h], dyh[h], uh[h]);
-              auxh[h] = dzh[h];
-            }
-          }
-        }
+        packed_dist<BIN, BOX, ARITH, NW>(ax[r], ay[r], az[r], X, Y, Z, zz, negzero, d2h, auxh);
 #pragma unroll
         for (int h = 0; h < 2; h++) {
           bool ok = d2h[h] < s2lim;
@@ -815,6 +887,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   constexpr int kThreads = BlockShape<T>::kThreads, kWarpsPerBlock = BlockShape<T>::kWarps;
   constexpr int NW = QFmt<BIN, BOX, WT>::NW;
   constexpr bool kPacked = PairLoop<T, BIN, BOX, WT>::kPacked;
+  constexpr bool kDense = FCFC_DENSE && kPacked && !GENERIC && SMEMHIST && BIN != BIN_SPI && RMAX >= 2;     // see do_chunk_dense
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
   const SmemPlan pl = make_smem_plan<T, WT>(P.ntot, P.nstab * (P.swidth ? 2 : 1), P.nptab * (P.pwidth ? 2 : 1),
@@ -906,7 +979,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
 
     // One contiguous range [b, e) of secondary points with per-axis image shifts.
     // sa: shift added to the primaries, sb: shift added to the secondaries (the lower point gets +L).
-    auto sweep_range = [&](int b, int e, T sax, T say, T saz, T sbx, T sby, T sbz, bool self) {
+    auto sweep_range = [&](int b, int e, T sax, T say, T saz, T sbx, T sby, T sbz, bool self, bool dense) {
       T ax[RMAX], ay[RMAX], az[RMAX];
 #pragma unroll
       for (int r = 0; r < RMAX; r++) {
@@ -952,10 +1025,15 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
+#define FCFC_DENSE(RR) do_chunk_dense<T, BIN, BOX, ARITH, RR, NW, RMAX>(P, Q, ub, F.hist_s, lane, sbuf, j, nj, ax, ay, az, s2lim, negzero)
 #define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane, s2lim, negzero)
           for (int j = 0;;) {
             if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
-            else if (RMAX == 4) {
+            else if (kDense && dense && nr >= RMAX - 1) {  // every pair in range: binned in place (full or nearly full tiles)
+              if constexpr (kDense) {
+                if (nr == RMAX) j = FCFC_DENSE(RMAX); else j = FCFC_DENSE(RMAX - 1);
+              }
+            } else if (RMAX == 4) {
               switch (nr) {                               // partially filled tiles evaluate only the primaries they hold
                 case 1: j = FCFC_CHUNK(1, false); break;
                 case 2: j = FCFC_CHUNK(2, false); break;
@@ -968,6 +1046,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
             ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, kPacked ? 2 * RMAX : RMAX, P.qkeep);
           }
 #undef FCFC_CHUNK
+#undef FCFC_DENSE
         }
         b = piece_end;
       }
@@ -980,11 +1059,18 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
     const int nq = (P.periodic ? 3 : 1) * P.nrows, qfirst = P.isauto ? -1 : 0;
     const int qlo = qfirst + (int) ((long long) (nq - qfirst) * split / P.nsplit);
     const int qhi = qfirst + (int) ((long long) (nq - qfirst) * (split + 1) / P.nsplit);
-    for (int q = qlo; q < qhi; q++) {
+    // With dense cells (do_chunk_dense) the z run of a sweep is cut into three pieces -- before, inside and after the
+    // row's dense cells -- enumerated by the same loop (qq = 3 q + piece), so that nothing but the loop counter stays
+    // live across a sweep: registers are what the pair loops are short of.
+    constexpr int kPieces = kDense ? 3 : 1;
+    for (int qq = kPieces * qlo; qq < kPieces * qhi; qq++) {
+      const int q = kDense ? (qq >= 0 ? qq / 3 : -1) : qq, piece = kDense ? qq - 3 * q : 0;
       int b, e;
       T sax = 0, say = 0, saz = 0, sbx = 0, sby = 0, sbz = 0;
-      if (q < 0) { b = t0; e = P.cell_start2[cell + 1]; }
-      else {
+      if (q < 0) {
+        if (piece != 0) continue;
+        b = t0; e = P.cell_start2[cell + 1];
+      } else {
         const int ri = P.periodic ? q / 3 : q, img = P.periodic ? q - 3 * ri : 1;
         const int4 row = s_rows[ri];
         int jx = ix + row.x, jy = iy + row.y;
@@ -1000,11 +1086,29 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           zlo = max(zlo, 0); zhi = min(zhi, ncz - 1);
         }
         if (zlo > zhi) continue;
+        if (kDense) {
+          // the dense cells of the row [dlo, dhi], through the same image mapping; none: dlo = zhi + 1 (piece 0 is everything)
+          int dlo = zhi + 1, dhi = zhi;
+          if (P.rows_in != nullptr) {
+            const int2 in = __ldg(&P.rows_in[ri]);
+            int lo = iz + in.x, hi = iz + in.y;
+            if (P.periodic) {
+              if (img == 0) { hi = min(hi, -1) + ncz; lo += ncz; }
+              else if (img == 2) { lo = max(lo, ncz) - ncz; hi -= ncz; }
+            }
+            lo = max(lo, zlo); hi = min(hi, zhi);
+            if (lo <= hi) { dlo = lo; dhi = hi; }
+          }
+          if (piece == 0) zhi = dlo - 1;
+          else if (piece == 1) { zlo = dlo; zhi = dhi; }
+          else zlo = dhi + 1;
+          if (zlo > zhi) continue;
+        }
         const int rowbase = (jx * ncy + jy) * ncz;
         b = P.cell_start2[rowbase + zlo]; e = P.cell_start2[rowbase + zhi + 1];
       }
       if (b >= e) continue;
-      sweep_range(b, e, sax, say, saz, sbx, sby, sbz, q < 0);
+      sweep_range(b, e, sax, say, saz, sbx, sby, sbz, q < 0, piece == 1);       // (a single call site keeps the pair loops in the instruction cache)
     }
   }
   // whatever is still queued

@@ -464,6 +464,26 @@ static std::vector<int4> build_stencil(const Grid &g, const Reach &R, bool half)
 
 // Choose the number of cells: cells of side reach/k, k picked by a simple cost model
 // (candidate evaluations per primary point, tile fill of the primary cells, per-range overhead).
+// For every stencil row the sub-range of dz whose cells lie entirely within the maximum separation of every point of
+// the tile's cell: the largest distance between a point of cell 0 and a point of cell (dx, dy, dz) is the norm of
+// ((|dx|+1) csx, (|dy|+1) csy, (|dz|+1) csz).  A small margin keeps points that sit on a cell face out of doubt; the
+// kernel keeps its range test anyway (count_kernel.cuh, do_chunk_dense).  Empty ranges are (1, 0).
+static std::vector<int2> stencil_inside(const Grid &g, const std::vector<int4> &rows, double s2max) {
+  std::vector<int2> in(rows.size());
+  const double lim = s2max * (1.0 - 1e-4);
+  for (size_t i = 0; i < rows.size(); i++) {
+    const double ex = (std::abs(rows[i].x) + 1) * g.cs[0], ey = (std::abs(rows[i].y) + 1) * g.cs[1];
+    int m = -1;                 // largest |dz| that is inside
+    while (true) {
+      const double ez = (m + 2) * g.cs[2];
+      if (ex * ex + ey * ey + ez * ez < lim) m++; else break;
+    }
+    const int lo = std::max(-m, rows[i].z), hi = std::min(m, rows[i].w);
+    in[i] = (m >= 0 && lo <= hi) ? make_int2(lo, hi) : make_int2(1, 0);
+  }
+  return in;
+}
+
 static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[3], const double hi[3],
                         double n1, double n2, int tile, bool half) {
   Grid best; double best_cost = 1e300;
@@ -589,8 +609,9 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const size_t sz_stab = (size_t) nstab * sw, sz_ptab = (size_t) nptab * pw, sz_mu = (bintype == BIN_SMU) ? (size_t) nmu * nmu : 0;
   const size_t sz_s2 = (ns + 1) * sizeof(T), sz_pb = np ? (np + 1) * sizeof(T) : 0, sz_rows = rows.size() * sizeof(int4);
   auto al = [](size_t v) { return (v + 255) & ~(size_t) 255; };
+  const size_t sz_rin = rows.size() * sizeof(int2);
   const size_t o_stab = 0, o_ptab = o_stab + al(sz_stab), o_mu = o_ptab + al(sz_ptab), o_s2 = o_mu + al(sz_mu),
-               o_pb = o_s2 + al(sz_s2), o_rows = o_pb + al(sz_pb), o_hist = o_rows + al(sz_rows),
+               o_pb = o_s2 + al(sz_s2), o_rows = o_pb + al(sz_pb), o_rin = o_rows + al(sz_rows), o_hist = o_rin + al(sz_rin),
                o_cnt = o_hist + al(ntot * 8), o_end = o_cnt + 256;
   std::vector<unsigned char> hbuf(o_end, 0);
   memcpy(&hbuf[o_stab], b->stab, sz_stab);
@@ -599,6 +620,10 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   memcpy(&hbuf[o_s2], s2bin, sz_s2);
   if (sz_pb) memcpy(&hbuf[o_pb], pbin, sz_pb);
   if (sz_rows) memcpy(&hbuf[o_rows], rows.data(), sz_rows);
+  if (sz_rin && bintype != BIN_SPI) {
+    const std::vector<int2> rin = stencil_inside(g, rows, s2max);
+    memcpy(&hbuf[o_rin], rin.data(), sz_rin);
+  }
   unsigned char *dbuf = nullptr;
   CUDA_TRY(pool_alloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(cudaMemcpy(dbuf, hbuf.data(), o_end, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
@@ -701,6 +726,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     const int ks = pick(2.5 * 3e-7 * (ns + 1), ns), km = pick(2.2 * (b->periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
     P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
     P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
+    P.fb_smul = 1u << (32 - ks); P.fb_mmul = 1u << (32 - km);
+    P.fb_bias = (0x4B000000u >> ks) + ((bintype == BIN_SMU) ? (0x4B000000u >> km) * (unsigned int) ns : 0u);
     if (ks < 6 || km < 6) P.stab_is_sqrt = 0;   // too many bins for the fixed-point trick: use the exact path
   }
   // accepted-pair queues: the deepest depth (a multiple of 4, <= 64) that fits next to the histogram and tables
@@ -742,6 +769,11 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
+  // dense cells are binned in place by the packed float pair loop of the variants whose drain computes its bins
+  // (count_kernel.cuh: kDense, do_chunk_dense)
+  const bool dense = is_float && !withwt && bintype != BIN_SPI && (b->periodic || bintype == BIN_ISO) && !v.generic && v.smem_hist &&
+                     P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt) && sz_rin && !getenv("FCFC_GPU_NO_DENSE");
+  P.rows_in = dense ? reinterpret_cast<const int2 *>(dbuf + o_rin) : nullptr;
   P.qdepth = depth;
   P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
   if (const char *ek = getenv("FCFC_GPU_QKEEP")) P.qkeep = std::max(0, std::min(atoi(ek), depth / 2));       // experiment hook
