@@ -41,6 +41,13 @@ WORKLOADS = {
     "c4_box_smu_clustered_1e7": dict(n=10_000_000, box=2000.0, bintype=1, nmu=120, clustered=True,
                                      desc="FCFC_2PT_BOX xi(s,mu) 10^7 clustered pts (Neyman-Scott, sigma=1.5, 20% background) L=2000 40x120 bins DD"),
 }
+# configs[2] of BASELINE.json: FCFC_2PT survey mode, weighted DD/DR/RR, xi(s_perp, pi) (and w_p from it on the host).
+# A step is the three pair counts.  Double precision: the reference's default build.
+SURVEY_WORKLOADS = {
+    "c3_svy_spi_wt_2e6_2e7": dict(nd=2_000_000, nr=20_000_000, smax=40.0, ds=2.0, pmax=80.0, dpi=1.0,
+                                  desc="FCFC_2PT weighted DD+DR+RR, xi(s_perp,pi): 2x10^6 data + 2x10^7 randoms, 20 s_perp x 80 pi bins, "
+                                       "60 deg x 30 deg patch at 1000-1700 Mpc/h comoving (coordinates already converted)"),
+}
 METRIC = "pair_evals_per_sec"
 UNIT = "pair evaluations/s"
 KAPPA_FILE = os.path.join(ROOT, "profiles", "workload_kappa.json")
@@ -114,6 +121,202 @@ class ClockSampler:
         return out
 
 
+def make_survey(n, seed, shrink=1.0):
+    """Comoving coordinates + weights of a survey patch: RA in [120, 120 + 60 g) deg, sin(dec) in [0, 0.5 g), uniform in
+    volume between 1000 Mpc/h and the radius that keeps the volume fraction g^3 of the full 1000-1700 Mpc/h shell
+    (g = shrink: bounded CPU samples keep the number density of the full workload)."""
+    rng = np.random.default_rng(seed)
+    ra = np.deg2rad(rng.uniform(120.0, 120.0 + 60.0 * shrink, n))
+    sd = rng.uniform(0.0, 0.5 * shrink, n)
+    cd = np.sqrt(1.0 - sd * sd)
+    d = np.cbrt(rng.uniform(1000.0 ** 3, 1000.0 ** 3 + shrink * (1700.0 ** 3 - 1000.0 ** 3), n))
+    return [np.ascontiguousarray(a) for a in (d * cd * np.cos(ra), d * cd * np.sin(ra), d * sd, rng.uniform(0.75, 1.25, n))]
+
+
+def run_survey_reference(args, wl):
+    """The unmodified reference (count_pairs of DD, DR, RR) on a bounded sample of the survey workload: 1/20 of the
+    objects in 1/20 of the volume (same number densities).  Job-equivalent value: evaluations of the full job per
+    unit of weighted in-range pair sum (profiles/workload_kappa.json) x the sample's weighted sum / seconds."""
+    from oracle import refdrv
+    frac = args.cpu_sample / float(wl["nr"]) if args.cpu_sample < wl["nr"] else 1.0
+    frac = min(frac, 1.0)
+    nd, nr = max(1000, int(wl["nd"] * frac)), max(1000, int(wl["nr"] * frac))
+    g = frac ** (1.0 / 3.0)
+    D, R = make_survey(nd, 7, g), make_survey(nr, 8, g)
+    prec = "flt" if args.prec == "float" else "dbl"
+    flav = refdrv.best_simd_flavour(prec)
+    p, isa = flav.split("_")
+    cores = os.cpu_count() or 1
+    nrep = max(1, args.steps if args.impl == "reference" else 1)
+    warm = args.warmup if args.impl == "reference" else 0
+    times, wsum = [], 0.0
+    for it in range(warm + nrep):
+        r = refdrv.run_reference([tuple(D), tuple(R)], periodic=False, prec=p, isa=isa, pairs=["DD", "DR", "RR"], bintype=2,
+                                 smin=0.0, smax=wl["smax"], ds=wl["ds"], pmin=0.0, pmax=wl["pmax"], dpi=wl["dpi"], threads=cores)
+        if it >= warm:
+            times.append(sum(q.t_count for q in r.pairs))
+        wsum = float(sum(q.cnt.sum() for q in r.pairs))
+    t = float(np.mean(times))
+    kappa = 10.0
+    try:
+        kappa = json.load(open(KAPPA_FILE)).get(args.workload, {}).get("evals_per_weighted_pair", kappa)
+    except Exception:
+        pass
+    return dict(seconds=t, wsum=wsum, value=kappa * wsum / t, cores=cores, flavour=flav,
+                sample=f"{nd} data + {nr} randoms in {frac:.3g} of the survey volume (same densities and bins), count_pairs of "
+                       f"DD+DR+RR only, reference build {flav}, OMP_NUM_THREADS={cores}, weighted in-range sum={wsum:.6g}, {t:.3f} s; "
+                       f"value = evals_per_weighted_pair({kappa:.3f}) x sum / s")
+
+
+def bench_survey(args):
+    """configs[2]: weighted survey counts in double precision; same JSON contract as the box workloads."""
+    wl = SURVEY_WORKLOADS[args.workload]
+    rank, world, local = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("LOCAL_RANK", "0"))
+    prec = "double" if args.prec_given is None else args.prec
+    args.prec = prec
+    config = {"workload": f"{args.workload}: {wl['desc']}", "n_data": wl["nd"], "n_random": wl["nr"],
+              "bins": f"{int(wl['smax'] / wl['ds'])} s_perp x {int(wl['pmax'] / wl['dpi'])} pi", "arith": "fma" if args.arith else "scalar",
+              "l2": "inputs (cell-sorted double4 randoms: 640 MB) larger than the 126 MB L2",
+              "parallelism": f"primary work items split over {world} rank(s), secondary replicated, NCCL all-reduce of the histograms"}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = run_survey_reference(args, wl)
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": r["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+                          "warmup": args.warmup, "ms_per_step": r["seconds"] * 1e3, "higher_is_better": True, "scaling": "strong",
+                          "vs_baseline": None, "dtype": "f32" if prec == "float" else "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
+                          "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    import torch
+    import fcfc_b200 as F
+    dist = None
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = torch.device("cuda", local)
+    F.init(devices=[local])
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    bins = F.Bins(periodic=False, prec=prec, arith=args.arith, bintype=2, smin=0.0, smax=wl["smax"], ds=wl["ds"],
+                  pmin=0.0, pmax=wl["pmax"], dpi=wl["dpi"])
+    npdt = np.float32 if prec == "float" else np.float64
+    host = []
+    for n, seed in ((wl["nd"], 1), (wl["nr"], 2)):
+        pinned = [torch.from_numpy(a.astype(npdt)).pin_memory() for a in make_survey(n, seed)]
+        host.append((pinned, [p.numpy() for p in pinned]))
+    ntot = bins.ntot
+    dev_hist = [torch.zeros(ntot, dtype=torch.float64, device=dev) for _ in range(3)]
+    PAIRS = ((0, 0), (0, 1), (1, 1))          # DD, DR, RR
+
+    def count_all(cats):
+        ev, nl, kms, out = 0, 0, 0.0, []
+        for k, (i, j) in enumerate(PAIRS):
+            c = F.count_pairs(cats[i], None if i == j else cats[j], bins, withwt=True, part=rank, nparts=world,
+                              dev_hist_ptr=dev_hist[k].data_ptr())
+            st = F.stats()
+            ev += st["pair_evals"]; nl += st["kernel_launches"]; kms += st["ms_count"]
+            if dist is not None:
+                dist.all_reduce(dev_hist[k])
+                c = dev_hist[k].cpu().numpy()
+            out.append(c)
+        return out, ev, nl, kms, st
+
+    cats = [F.Catalog(*h[1], bins=bins) for h in host]
+    for _ in range(max(3, args.warmup)):
+        counts, _, _, _, st = count_all(cats)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    evals = launches = 0
+    kern_ms = 0.0
+    for _ in range(args.steps):
+        counts, ev, nl, kms, st = count_all(cats)
+        evals += ev; launches += nl; kern_ms += kms
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if rank == 0 else None
+    t_ms = torch.tensor([ms], dtype=torch.float64, device=dev)
+    evt = torch.tensor([float(evals)], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t_ms, op=dist.ReduceOp.MAX)
+        dist.all_reduce(evt, op=dist.ReduceOp.SUM)
+    ms, total_evals = float(t_ms.item()), float(evt.item())
+    value = total_evals / (ms * 1e-3)
+    for c in cats:
+        c.destroy()
+
+    # ---- end to end: upload both catalogues from pinned host memory, three counts, histograms back ----
+    def step_e2e():
+        cc = [F.Catalog(*h[1], bins=bins) for h in host]
+        out, ev, _, _, _ = count_all(cc)
+        for c in cc:
+            c.destroy()
+        return out, ev
+    step_e2e()
+    barrier()
+    e0.record()
+    ev_e2e = 0.0
+    for _ in range(args.steps):
+        c2, ev = step_e2e()
+        ev_e2e += ev
+    e1.record()
+    barrier()
+    t2 = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    ev2 = torch.tensor([ev_e2e], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(t2, op=dist.ReduceOp.MAX)
+        dist.all_reduce(ev2, op=dist.ReduceOp.SUM)
+    e2e_value = float(ev2.item()) / (float(t2.item()) * 1e-3)
+    rel = max(float(np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))) for a, b in zip(c2, counts))
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+    wsum = float(sum(c.sum() for c in counts))
+    # roofline: FP64 issue peak / 5 instructions per evaluation up to the first range test (dot product 3, s1 + s2, s - t)
+    peak64 = F.measure_fp64_peak() if prec == "double" else F.measure_fp32_peak()[0]
+    achieved = (evals * world / args.steps) / (kern_ms / args.steps * 1e-3) * 5.0 * 1e-12 if world == 1 else None
+    roofline = {"bound": "fp64_issue" if prec == "double" else "fp32_issue", "achieved": achieved, "peak": peak64 * 1e-12,
+                "unit": "T FP instr/s (5 per pair evaluation)", "frac": (achieved / (peak64 * 1e-12)) if achieved else None, "traffic": None,
+                "algorithmic_bytes": 32 * (wl["nd"] + wl["nr"]), "kernel": "fcfc::count_kernel (survey, weighted)", "kernel_ms": kern_ms / args.steps,
+                "peak_source": "measured live: DFMA stream on all SMs (fcfc_gpu_measure_fp64_peak)"}
+    kappa = total_evals / args.steps / max(wsum, 1e-300)
+    try:
+        allk = json.load(open(KAPPA_FILE)) if os.path.exists(KAPPA_FILE) else {}
+        allk[args.workload] = {"evals_per_weighted_pair": kappa, "weighted_pairs_in": wsum}
+        json.dump(allk, open(KAPPA_FILE, "w"), indent=1)
+    except Exception:
+        pass
+    cpu = None
+    if world == 1 and not args.no_cpu:
+        try:
+            r = run_survey_reference(args, wl)
+            cpu = {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]}
+        except Exception as ex:
+            cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
+    isz = np.dtype(npdt).itemsize
+    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                      "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                      "dtype": "f32" if prec == "float" else "f64", "data": "synthetic", "config": config, "clocks": clocks,
+                      "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * (wl["nd"] + wl["nr"]) * isz),
+                              "d2h_bytes_per_step": int(3 * ntot * 8), "ms_per_step": float(t2.item()) / args.steps,
+                              "max_rel_diff_vs_resident": rel},
+                      "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                      "weighted_pairs_in": wsum, "evals_per_weighted_pair": kappa, "grid": st["ncell"], "work_items": st["nitem"]}))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
 def run_reference_arm(args, wl, sample_n, prec):
     """Time the unmodified reference (count_pairs only) on a bounded sample of the workload."""
     from oracle import refdrv
@@ -153,12 +356,18 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c2_box_smu_1e7", choices=sorted(WORKLOADS))
-    ap.add_argument("--prec", default="float", choices=["float", "double"])
+    ap.add_argument("--workload", default="c2_box_smu_1e7", choices=sorted(WORKLOADS) + sorted(SURVEY_WORKLOADS))
+    ap.add_argument("--prec", default=None, choices=["float", "double"], help="default: float for the box workloads, double for the survey")
     ap.add_argument("--arith", type=int, default=1, help="0 scalar-parity order, 1 FMA order")
     ap.add_argument("--cpu-sample", type=int, default=400_000, help="points of the bounded CPU sample")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     args = ap.parse_args()
+    args.prec_given = args.prec
+    if args.workload in SURVEY_WORKLOADS:
+        if args.cpu_sample == 400_000:
+            args.cpu_sample = 1_000_000        # randoms of the bounded survey sample
+        return bench_survey(args)
+    args.prec = args.prec or "float"
     wl = WORKLOADS[args.workload]
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

@@ -80,6 +80,8 @@ def lib():
         L.fcfc_gpu_bins_free.argtypes = [C.c_void_p]
         L.fcfc_gpu_measure_fp32_peak.restype = C.c_double
         L.fcfc_gpu_measure_fp32_peak.argtypes = [C.POINTER(C.c_double)]
+        L.fcfc_gpu_measure_fp64_peak.restype = C.c_double
+        L.fcfc_gpu_measure_fp64_peak.argtypes = []
         L.fcfc_gpu_init.argtypes = [C.c_int, C.c_void_p, C.c_int]
         _lib = L
     return _lib
@@ -282,3 +284,11 @@ def measure_fp32_peak() -> tuple[float, float]:
     if v <= 0:
         raise FcfcGpuError("FP32 peak measurement failed (no device?)")
     return v, clk.value
+
+
+def measure_fp64_peak() -> float:
+    """FP64 lane-instructions per second (DFMA stream on all SMs)."""
+    v = lib().fcfc_gpu_measure_fp64_peak()
+    if v <= 0:
+        raise FcfcGpuError("FP64 peak measurement failed (no device?)")
+    return v

@@ -20,7 +20,44 @@ __global__ void __launch_bounds__(1024) ffma_kernel(float *out, float a, float b
   for (int i = 0; i < 8; i++) s += x[i];
   out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+__global__ void __launch_bounds__(1024) dfma_kernel(double *out, double a, double b) {
+  double x[8];
+#pragma unroll
+  for (int i = 0; i < 8; i++) x[i] = threadIdx.x * 1e-3 + i;
+  for (int it = 0; it < kIters / 4; it++) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) x[i] = fma(x[i], a, b);
+  }
+  double s = 0;
+#pragma unroll
+  for (int i = 0; i < 8; i++) s += x[i];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
 }  // namespace
+
+// FP64 issue peak (DFMA stream): the denominator for the double-precision kernels.
+extern "C" double fcfc_gpu_measure_fp64_peak(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  const int grid = p.multiProcessorCount * 2;
+  double *out = nullptr;
+  if (cudaMalloc(&out, sizeof(double) * grid * 1024) != cudaSuccess) return 0;
+  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1);
+  double best = 0;
+  for (int rep = 0; rep < 6; rep++) {
+    cudaEventRecord(e0);
+    dfma_kernel<<<grid, 1024>>>(out, 1.0001, 0.5);
+    cudaEventRecord(e1);
+    if (cudaEventSynchronize(e1) != cudaSuccess) { best = 0; break; }
+    float ms = 0; cudaEventElapsedTime(&ms, e0, e1);
+    const double rate = (double) grid * 1024 * (kIters / 4) * 8 / (ms * 1e-3);
+    if (rep > 0 && rate > best) best = rate;
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  return best;
+}
 
 extern "C" double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out) {
   int dev = 0;

@@ -159,6 +159,8 @@ void fcfc_gpu_bins_free(fcfc_gpu_bins_owner *o);
 /* Measured FP32 instruction issue peak of device 0 (lane-instructions per second of a dependent-
  * free FFMA stream) -- the denominator of the pair-evaluation roofline. */
 double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out);
+/* The same for FP64 (DFMA stream): the denominator for the double-precision kernels. */
+double fcfc_gpu_measure_fp64_peak(void);
 
 #ifdef __cplusplus
 }
