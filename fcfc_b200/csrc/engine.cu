@@ -620,9 +620,11 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   memcpy(&hbuf[o_s2], s2bin, sz_s2);
   if (sz_pb) memcpy(&hbuf[o_pb], pbin, sz_pb);
   if (sz_rows) memcpy(&hbuf[o_rows], rows.data(), sz_rows);
+  int dense_rows = 0;
   if (sz_rin && bintype != BIN_SPI) {
     const std::vector<int2> rin = stencil_inside(g, rows, s2max);
     memcpy(&hbuf[o_rin], rin.data(), sz_rin);
+    for (const int2 &r : rin) dense_rows += r.x <= r.y;
   }
   unsigned char *dbuf = nullptr;
   CUDA_TRY(pool_alloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
@@ -799,6 +801,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];
   g_stats.nitem = my_items;
+  g_stats.dense_rows = dense ? dense_rows : 0;
   cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
   pool_free(dbuf); pool_free(d_order);
   return 0;

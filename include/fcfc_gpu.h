@@ -102,7 +102,7 @@ typedef struct {
   uint32_t kernel_launches; /* number of kernels of this library launched by the call            */
   int32_t ncell[3];     /* cell grid used                                                         */
   int32_t nitem;        /* number of (cell, tile) work items                                      */
-  int32_t reserved;
+  int32_t dense_rows;   /* stencil rows with cells binned in place (dense-cell path), 0 if unused */
 } fcfc_gpu_stats;
 
 /* Bind the calling process to CUDA devices.  ndev <= 0: all visible devices.  `devices` may be

@@ -78,6 +78,33 @@ def test_medium_box_vs_oracle(gpu, prec, kw):
     np.testing.assert_array_equal(got, oracle.count(ob, oracle.preprocess(ob, cat)))
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("kw", [dict(bintype=1, smax=42.0, ds=1.0, nmu=50), dict(bintype=0, smax=42.0, ds=1.5)])
+def test_dense_cells_vs_oracle(gpu, kw, arith, monkeypatch):
+    """The dense-cell path (secondary cells entirely in range are binned in place by the pair loop, count_kernel.cuh:
+    do_chunk_dense) needs full tiles: 25k points in a box of 7^3 cells of a third of the maximum separation (forced
+    with FCFC_GPU_K) give ~73 points per cell and seven dense offsets.  Counts must equal the oracle's and those of
+    the same engine with the path switched off; auto and cross counts."""
+    a, b = box_catalog(25000, 100.0, 41, weights=False), box_catalog(20000, 100.0, 42, weights=False)
+    monkeypatch.setenv("FCFC_GPU_K", "3")
+    bins = gpu.Bins(periodic=True, prec="float", arith=arith, box=100.0, **kw)
+    ga, gb = gpu.Catalog(*a, bins=bins), gpu.Catalog(*b, bins=bins)
+    on = {}
+    for name, c2 in (("DD", None), ("DR", gb)):
+        on[name] = gpu.count_pairs(ga, c2, bins)
+        assert gpu.stats()["dense_rows"] > 0, "the dense path was not used"
+    monkeypatch.setenv("FCFC_GPU_NO_DENSE", "1")
+    for name, c2 in (("DD", None), ("DR", gb)):
+        off = gpu.count_pairs(ga, c2, bins)
+        assert gpu.stats()["dense_rows"] == 0
+        np.testing.assert_array_equal(on[name], off)
+    ga.destroy(); gb.destroy()
+    ob = oracle.setup(prec="f", periodic=True, arith=arith, box=100.0, **kw)
+    pa, pb = oracle.preprocess(ob, a), oracle.preprocess(ob, b)
+    np.testing.assert_array_equal(on["DD"], oracle.count(ob, pa))
+    np.testing.assert_array_equal(on["DR"], oracle.count(ob, pa, pb))
+
+
 @pytest.mark.parametrize("prec", ["double", "float"])
 def test_clustered_cuboid_vs_oracle(gpu, prec):
     cat = clustered_box_catalog(20000, 400.0, 32)
