@@ -321,6 +321,7 @@ def run_reference_arm(args, wl, sample_n, prec):
     """Time the unmodified reference (count_pairs only) on a bounded sample of the workload."""
     from oracle import refdrv
     dens = wl["n"] / wl["box"] ** 3
+    sample_n = max(sample_n, int(dens * (2.1 * 200.0) ** 3) + 1)      # the periodic sample box must exceed twice the maximum separation
     Ls = (sample_n / dens) ** (1.0 / 3.0)
     cat = make_catalog(wl, sample_n, Ls, seed=7)
     flav = refdrv.best_simd_flavour("flt" if prec == "float" else "dbl")
