@@ -53,6 +53,25 @@ UNIT = "pair evaluations/s"
 KAPPA_FILE = os.path.join(ROOT, "profiles", "workload_kappa.json")
 
 
+_OUT = None
+
+
+def claim_stdout():
+    """Keep stdout for the one JSON line of the contract: whatever else writes to file descriptor 1 from here on
+    (NCCL prints its version banner there) goes to stderr."""
+    global _OUT
+    if _OUT is None:
+        sys.stdout.flush()
+        _OUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _OUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def make_box(n, L, seed=20261017):
     rng = np.random.default_rng(seed)
     return [np.ascontiguousarray(rng.random(n) * L) for _ in range(3)]
@@ -188,6 +207,7 @@ def bench_survey(args):
                           "cpu_baseline": {"value": r["value"], "unit": UNIT, "cores": r["cores"], "kind": "reference", "sample": r["sample"]},
                           "e2e": {"value": r["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
+    claim_stdout()
     import torch
     import fcfc_b200 as F
     dist = None
@@ -305,14 +325,14 @@ def bench_survey(args):
         except Exception as ex:
             cpu = {"value": None, "unit": UNIT, "cores": os.cpu_count(), "kind": "reference", "sample": f"failed: {ex}"}
     isz = np.dtype(npdt).itemsize
-    print(json.dumps({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+    emit({"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                       "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
                       "dtype": "f32" if prec == "float" else "f64", "data": "synthetic", "config": config, "clocks": clocks,
                       "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": int(4 * (wl["nd"] + wl["nr"]) * isz),
                               "d2h_bytes_per_step": int(3 * ntot * 8), "ms_per_step": float(t2.item()) / args.steps,
                               "max_rel_diff_vs_resident": rel},
                       "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
-                      "weighted_pairs_in": wsum, "evals_per_weighted_pair": kappa, "grid": st["ncell"], "work_items": st["nitem"]}))
+                      "weighted_pairs_in": wsum, "evals_per_weighted_pair": kappa, "grid": st["ncell"], "work_items": st["nitem"]})
     if dist is not None:
         dist.destroy_process_group()
 
@@ -392,6 +412,7 @@ def main():
         return
 
     # ---------------------------------------------------------------- our arm
+    claim_stdout()
     import torch
     import fcfc_b200 as F
     dist = None
@@ -540,7 +561,7 @@ def main():
             "in_range_pairs": pairs_in, "in_range_pairs_per_sec": pairs_in / (ms / args.steps * 1e-3),
             "evals_per_inrange_pair": kappa, "dd_wall_time_s": float(t2.item()) / args.steps * 1e-3,
             "grid": st["ncell"], "work_items": st["nitem"]}
-    print(json.dumps(line))
+    emit(line)
     if dist is not None:
         dist.destroy_process_group()
 
