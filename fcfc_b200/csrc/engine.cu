@@ -773,7 +773,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
   // dense cells are binned in place by the packed float pair loop of the variants whose drain computes its bins
   // (count_kernel.cuh: kDense, do_chunk_dense)
-  const bool dense = is_float && !withwt && bintype != BIN_SPI && (b->periodic || bintype == BIN_ISO) && !v.generic && v.smem_hist &&
+  // (periodic boxes only: the survey's isotropic float counts could take it too, but no test exercises it there yet)
+  const bool dense = is_float && !withwt && bintype != BIN_SPI && b->periodic && !v.generic && v.smem_hist &&
                      P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt) && sz_rin && !getenv("FCFC_GPU_NO_DENSE");
   P.rows_in = dense ? reinterpret_cast<const int2 *>(dbuf + o_rin) : nullptr;
   P.qdepth = depth;
