@@ -23,7 +23,9 @@
 //     isotropic counts compute both bins from one rsqrt.approx with fixed-point edge detection; pairs
 //     within the error band of a bin edge are re-binned with the exact IEEE sequence of the reference
 //     (results are bit-exact).  The histogram is per block in shared memory (32-bit counters flushed
-//     lock-free to 64-bit global counters; FP64 sums for weighted counts).
+//     lock-free to 64-bit global counters; FP64 sums for weighted counts);
+//   * secondary cells that lie entirely within range of the tile's cell ("dense" cells, marked by the host per
+//     stencil row) skip the stacks: the pair loop bins their pairs in place (do_chunk_dense).
 //
 // No tensor cores: the work is FP32/FP64 CUDA-core arithmetic plus shared-memory atomics.
 #pragma once
@@ -691,44 +693,44 @@ __device__ __forceinline__ f32x2 mul2_uncontracted(f32x2 a, f32x2 b, float negze
 template <int BIN, bool BOX, int ARITH, int NW>
 __device__ __forceinline__ void packed_dist(const float axr, const float ayr, const float azr, const f32x2 X, const f32x2 Y, const f32x2 Z,
                                             const float (&zz)[2], const float negzero, float (&d2h)[2], float (&auxh)[2]) {
-    const f32x2 dx = sub2(pk2(axr, axr), X), dy = sub2(pk2(ayr, ayr), Y);
-    if (NW == 1) {                            // isotropic: everything packed, only d2 is kept
-      const f32x2 dz = sub2(pk2(azr, azr), Z);
-      const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
-      f32x2 d2;
-      if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
-      else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
-      else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
-      upk2(d2, d2h[0], d2h[1]);
-      auxh[0] = auxh[1] = 0.0f;
-    } else {
-      // two-word entries (d2, aux) are pushed with one 64-bit store each: the last operation of the d2 chain and
-      // the z difference are scalar, so that d2_h and aux_h can be produced side by side in registers
-      float dzh[2], dyh[2];
-      dzh[0] = __fsub_rn(azr, zz[0]); dzh[1] = __fsub_rn(azr, zz[1]);
-      upk2(dy, dyh[0], dyh[1]);
-      if (BIN == BIN_SPI) {                   // box (s_perp, pi): metric_common.c:157-165, 416-424
-        float mxh[2], myh[2];
-        if (ARITH == ARITH_SCALAR) {
-          upk2(mul2_uncontracted(dx, dx, negzero), mxh[0], mxh[1]); upk2(mul2_uncontracted(dy, dy, negzero), myh[0], myh[1]);
-        } else upk2(mul2(dx, dx), mxh[0], mxh[1]);
+  const f32x2 dx = sub2(pk2(axr, axr), X), dy = sub2(pk2(ayr, ayr), Y);
+  if (NW == 1) {                            // isotropic: everything packed, only d2 is kept
+    const f32x2 dz = sub2(pk2(azr, azr), Z);
+    const f32x2 dz2 = (ARITH == ARITH_SCALAR) ? mul2_uncontracted(dz, dz, negzero) : mul2(dz, dz);
+    f32x2 d2;
+    if (ARITH == ARITH_SCALAR) d2 = add2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), dz2);      // :170-172
+    else if (BOX) d2 = fma2(dy, dy, fma2(dx, dx, dz2));                               // :426-430
+    else d2 = fma2(dz, dz, fma2(dy, dy, mul2(dx, dx)));                               // 2pt/:330-333
+    upk2(d2, d2h[0], d2h[1]);
+    auxh[0] = auxh[1] = 0.0f;
+  } else {
+    // two-word entries (d2, aux) are pushed with one 64-bit store each: the last operation of the d2 chain and
+    // the z difference are scalar, so that d2_h and aux_h can be produced side by side in registers
+    float dzh[2], dyh[2];
+    dzh[0] = __fsub_rn(azr, zz[0]); dzh[1] = __fsub_rn(azr, zz[1]);
+    upk2(dy, dyh[0], dyh[1]);
+    if (BIN == BIN_SPI) {                   // box (s_perp, pi): metric_common.c:157-165, 416-424
+      float mxh[2], myh[2];
+      if (ARITH == ARITH_SCALAR) {
+        upk2(mul2_uncontracted(dx, dx, negzero), mxh[0], mxh[1]); upk2(mul2_uncontracted(dy, dy, negzero), myh[0], myh[1]);
+      } else upk2(mul2(dx, dx), mxh[0], mxh[1]);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(mxh[h], myh[h]) : __fmaf_rn(dyh[h], dyh[h], mxh[h]);
-          auxh[h] = fabsf(dzh[h]);
-        }
-      } else {                                // box (s, mu): :170-172 / :426-430
-        const float dz2h[2] = {__fmul_rn(dzh[0], dzh[0]), __fmul_rn(dzh[1], dzh[1])};
-        float uh[2];
-        if (ARITH == ARITH_SCALAR) upk2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), uh[0], uh[1]);
-        else upk2(fma2(dx, dx, pk2(dz2h[0], dz2h[1])), uh[0], uh[1]);
+      for (int h = 0; h < 2; h++) {
+        d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(mxh[h], myh[h]) : __fmaf_rn(dyh[h], dyh[h], mxh[h]);
+        auxh[h] = fabsf(dzh[h]);
+      }
+    } else {                                // box (s, mu): :170-172 / :426-430
+      const float dz2h[2] = {__fmul_rn(dzh[0], dzh[0]), __fmul_rn(dzh[1], dzh[1])};
+      float uh[2];
+      if (ARITH == ARITH_SCALAR) upk2(add2(mul2_uncontracted(dx, dx, negzero), mul2_uncontracted(dy, dy, negzero)), uh[0], uh[1]);
+      else upk2(fma2(dx, dx, pk2(dz2h[0], dz2h[1])), uh[0], uh[1]);
 #pragma unroll
-        for (int h = 0; h < 2; h++) {
-          d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(uh[h], dz2h[h]) : __fmaf_rn(dyh[h], dyh[h], uh[h]);
-          auxh[h] = dzh[h];
-        }
+      for (int h = 0; h < 2; h++) {
+        d2h[h] = (ARITH == ARITH_SCALAR) ? __fadd_rn(uh[h], dz2h[h]) : __fmaf_rn(dyh[h], dyh[h], uh[h]);
+        auxh[h] = dzh[h];
       }
     }
+  }
 }
 
 // Variants whose pair loop runs packed: float, isotropic bins, unweighted (one word per queue entry).  Their staging
