@@ -886,7 +886,7 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
 template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int RMAX>
 __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const __grid_constant__ CountParams<T> P) {
   extern __shared__ __align__(16) unsigned char smem[];
-  constexpr int kThreads = BlockShape<T>::kThreads, kWarpsPerBlock = BlockShape<T>::kWarps;
+  constexpr int kThreads = BlockShape<T>::kThreads;
   constexpr int NW = QFmt<BIN, BOX, WT>::NW;
   constexpr bool kPacked = PairLoop<T, BIN, BOX, WT>::kPacked;
   constexpr bool kDense = FCFC_DENSE && kPacked && !GENERIC && SMEMHIST && BIN != BIN_SPI && RMAX >= 2;     // see do_chunk_dense
@@ -1027,13 +1027,13 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
           if (jn < piece_end) { nxt = P.pos2[jn]; if (WT) nxtw = P.w2[jn]; }
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
-#define FCFC_DENSE(RR) do_chunk_dense<T, BIN, BOX, ARITH, RR, NW, RMAX>(P, Q, ub, F.hist_s, lane, sbuf, j, nj, ax, ay, az, s2lim, negzero)
+#define FCFC_CHUNK_DENSE(RR) do_chunk_dense<T, BIN, BOX, ARITH, RR, NW, RMAX>(P, Q, ub, F.hist_s, lane, sbuf, j, nj, ax, ay, az, s2lim, negzero)
 #define FCFC_CHUNK(RR, SF) do_chunk<T, BIN, BOX, WT, ARITH, GENERIC, RR, SF, NW, RMAX>(P, Q, ub, sbuf, wbuf, j, nj, ax, ay, az, ps, pw, c0, t0, lane, s2lim, negzero)
           for (int j = 0;;) {
             if (sf) j = FCFC_CHUNK(RMAX, true);           // rare: the tile against its own points
             else if (kDense && dense && nr >= RMAX - 1) {  // every pair in range: binned in place (full or nearly full tiles)
               if constexpr (kDense) {
-                if (nr == RMAX) j = FCFC_DENSE(RMAX); else j = FCFC_DENSE(RMAX - 1);
+                if (nr == RMAX) j = FCFC_CHUNK_DENSE(RMAX); else j = FCFC_CHUNK_DENSE(RMAX - 1);
               }
             } else if (RMAX == 4) {
               switch (nr) {                               // partially filled tiles evaluate only the primaries they hold
@@ -1048,7 +1048,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
             ub = drain_queue<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, F, Q, kPacked ? 2 * RMAX : RMAX, P.qkeep);
           }
 #undef FCFC_CHUNK
-#undef FCFC_DENSE
+#undef FCFC_CHUNK_DENSE
         }
         b = piece_end;
       }
