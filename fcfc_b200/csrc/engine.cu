@@ -746,7 +746,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd) & ~3);
   // preference order: everything in shared memory with deep queues > tables in global memory >
   // shallow queues > histogram in global memory (large tables / histograms are rare)
-  SmemPlan pl; int depth = 0; bool tabs_global = false; v.smem_hist = true;
+  SmemPlan pl{}; int depth = 0; bool tabs_global = false; v.smem_hist = true;
   const struct { bool sh, tg; int dmin; } tries[] = {{true, false, 16}, {true, true, 16}, {true, false, 8}, {true, true, 8},
                                                      {false, false, 16}, {false, true, 8}};
   // fast variants whose s and mu bins are computed never read the tables in the hot loop: leave them in

@@ -20,6 +20,9 @@
 * (default: the scalar order, bit-exact against the reference's scalar code path);
 * FCFC_GPU_DEVICES=0,1,... restricts the devices; FCFC_GPU_VERBOSE=1 prints engine diagnostics.
 *******************************************************************************/
+#ifndef _POSIX_C_SOURCE
+#define _POSIX_C_SOURCE 200809L         /* strdup, strtok_r (the reference's Makefile sets the same) */
+#endif
 #include "define.h"
 #include "eval_cf.h"
 #include "count_func.h"
