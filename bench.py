@@ -532,7 +532,9 @@ def main():
                 "frac": achieved / (peak_instr * 1e-12), "traffic": traffic, "traffic_unit": "bytes per launch (ncu dram__bytes_read+write)",
                 "algorithmic_bytes": 16 * wl["n"], "kernel": "fcfc::count_kernel", "kernel_ms": k_ms,
                 "peak_source": "measured live: FFMA stream on all SMs (fcfc_gpu_measure_fp32_peak); MEASURED_PEAKS.json has no FP32 figure",
-                "evals_per_sec_kernel": evals_per_launch / (k_ms * 1e-3), "r_eval_peak": peak_instr / 6.0}
+                "evals_per_sec_kernel": evals_per_launch / (k_ms * 1e-3), "r_eval_peak": peak_instr / 6.0,
+                # the same statement in flops: 8 flop per evaluation against 2 flop per FFMA lane
+                "flop_equivalent": {"achieved_tflops": evals_per_launch / (k_ms * 1e-3) * 8e-12, "peak_tflops": 2.0 * peak_instr * 1e-12}}
     kappa = evals["n"] / args.steps * world / max(pairs_in, 1) if world == 1 else total_evals / args.steps / max(pairs_in, 1)
     try:
         os.makedirs(os.path.dirname(KAPPA_FILE), exist_ok=True)
