@@ -23,6 +23,16 @@
 #include <thread>
 #include <vector>
 
+// Fixed-point scales 2^ks, 2^km of the fast bins (count_kernel.cuh, fast_bins): the flag band 2^-k must cover the error
+// budget with a factor >= 2 to spare, and bin * 2^k must stay below 2^23.  Pure host arithmetic, exported so that the
+// CPU tests can check the error budget against an emulation of the device arithmetic (tests/test_fastbin_budget.py).
+extern "C" void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km) {
+  auto pick = [](double need, int nbin) { int k = 20; while (k > 4 && (std::ldexp(1.0, -k) < need || (double) (nbin + 2) * std::ldexp(1.0, k) >= 8388608.0)) k--; return k; };
+  // (survey (s,mu): mu comes from two approximate reciprocal square roots and three converted terms, 9.5e-7 relative)
+  if (ks) *ks = pick(2.5 * 3e-7 * (ns + 1), ns);
+  if (km) *km = pick(2.2 * (periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
+}
+
 namespace fcfc {
 
 // ------------------------------------------------------------------------------------------
@@ -723,9 +733,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     if (getenv("FCFC_GPU_NO_TABLE_MATH")) P.mu_is_sqrt = P.stab_is_sqrt = P.ptab_is_ident = 0;
     // fixed-point scales of the fast bins (count_kernel.cuh, fast_bins): the flag band 2^-k must cover the error
     // budget with a factor >= 2 to spare, and bin * 2^k must stay below 2^23
-    auto pick = [](double need, int nbin) { int k = 20; while (k > 4 && (std::ldexp(1.0, -k) < need || (double) (nbin + 2) * std::ldexp(1.0, k) >= 8388608.0)) k--; return k; };
-    // (survey (s,mu): mu comes from two approximate reciprocal square roots and three converted terms, 9.5e-7 relative)
-    const int ks = pick(2.5 * 3e-7 * (ns + 1), ns), km = pick(2.2 * (b->periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
+    int ks = 0, km = 0;
+    fcfc_gpu_fastbin_scales(ns, nmu, b->periodic, &ks, &km);
     P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
     P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
     P.fb_smul = 1u << (32 - ks); P.fb_mmul = 1u << (32 - km);

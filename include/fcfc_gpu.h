@@ -161,6 +161,9 @@ void fcfc_gpu_bins_free(fcfc_gpu_bins_owner *o);
 double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out);
 /* The same for FP64 (DFMA stream): the denominator for the double-precision kernels. */
 double fcfc_gpu_measure_fp64_peak(void);
+/* Diagnostics: the fixed-point scales 2^ks, 2^km the counting kernels use for their computed s and mu bins
+ * (host arithmetic only; the CPU tests check the error budget behind them). */
+void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km);
 
 #ifdef __cplusplus
 }
