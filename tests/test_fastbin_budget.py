@@ -96,3 +96,93 @@ def test_unflagged_pairs_are_binned_exactly(ns, nmu, arith):
 
 def test_scales_of_the_bench_workload():
     assert scales(40, 120) == (14, 13)
+
+
+# ---------------------------------------------------------------------------------------------------
+# Survey (s, mu): the queued pair is (t, s1, s2) with t = 2 x1.x2 and s_i = |x_i|^2 (2pt/metric_common.c:169-184);
+# the drain rebuilds d2 = (s1 + s2) - t exactly as the pair loop did and takes pi = |s1 - s2| rsqrt(s1 + s2 + t) as the
+# line-of-sight separation (count_kernel.cuh: fast_inputs), i.e. one more approximate reciprocal square root and, in
+# double precision, three conversions to float; the host widens the mu band accordingly.
+def survey_exact(t, s1, s2, ns, nmu, arith, real):
+    nmu2 = real(nmu * nmu)
+    s = s1 + s2
+    d2 = s - t
+    d = s1 - s2
+    with np.errstate(divide="ignore", invalid="ignore"):
+        num = (d * d) / (s + t)                               # pi^2
+        if arith == 0:
+            m = np.where(d2 < np.finfo(real).eps, 0, np.trunc((num / d2) * nmu2)).astype(np.int64)
+        else:
+            q = num * nmu2
+            qn = (q / d2).astype(real)
+            # round toward zero: one ulp down when the rounded quotient overshot (checked in higher precision)
+            over = qn.astype(np.longdouble) * d2.astype(np.longdouble) > q.astype(np.longdouble)
+            qz = np.where(over, np.nextafter(qn, real(0)), qn)
+            m = np.where(qz < nmu2, np.trunc(qz), nmu * nmu).astype(np.int64)
+            m = np.where(d2 >= np.finfo(real).eps, m, 0)
+    sb = np.floor(np.sqrt(np.floor(np.maximum(d2, 0).astype(np.float64)))).astype(np.int64)
+    mb = np.floor(np.sqrt(m.astype(np.float64))).astype(np.int64)
+    ok = m < nmu * nmu
+    return d2, np.where(ok, sb, -1), np.where(ok, mb, -1)
+
+
+def survey_fast(t, s1, s2, ns, nmu, ks, km, delta1, delta2):
+    s = s1 + s2
+    d2f = np.maximum((s - t).astype(f32), f32(0))
+    df, stf = (s1 - s2).astype(f32), (s + t).astype(f32)
+    r1 = (1.0 / np.sqrt(stf.astype(np.float64)) * (1.0 + delta1)).astype(f32)
+    auxf = df * r1
+    r = (1.0 / np.sqrt(d2f.astype(np.float64) + 1e-30) * (1.0 + delta2)).astype(f32)
+    sr, mr = d2f * r, np.minimum(np.abs(auxf * r), f32(1.000002))
+    i_s = np.floor(sr.astype(np.float64) * 2.0 ** ks).astype(np.int64) + 1
+    i_m = np.floor(mr.astype(np.float64) * (nmu * 2.0 ** km)).astype(np.int64) + 1
+    flagged = ((i_s & ((1 << ks) - 4)) == 0) | ((i_m & ((1 << km) - 2)) == 0)
+    return i_s >> ks, i_m >> km, flagged
+
+
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("ns,nmu", [(40, 100), (40, 120), (100, 30)])
+def test_survey_unflagged_pairs_are_binned_exactly(ns, nmu, arith, real):
+    ks, km = scales(ns, nmu, periodic=0)
+    if ks < 6 or km < 6:
+        pytest.skip("exact path")
+    rng = np.random.default_rng(77 * ns + nmu + arith)
+    n = 500_000
+    # points at 200-340 from the observer in units of the s bin width (the rescaled survey), separations inside the range
+    r1 = rng.uniform(200.0, 340.0, n)
+    sep = rng.uniform(0.05, ns, n)
+    k = n // 2
+    sep[:k] = np.clip(rng.integers(1, ns + 1, k) + rng.normal(0, 1, k) * 2.0 ** rng.uniform(-24, -8, k), 0.05, ns * (1 - 1e-6))
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    v = rng.normal(size=(n, 3)); v /= np.linalg.norm(v, axis=1)[:, None]
+    x1 = (u * r1[:, None]).astype(real)
+    x2 = x1.astype(np.float64) + v * sep[:, None]
+    # a quarter of the pairs get nmu * mu planted next to an integer: mu is the cosine between the separation and the
+    # direction of x1 + x2, which depends on x2 itself -- a few fixed-point iterations settle it
+    q = n // 4
+    mu_t = np.clip((rng.integers(0, nmu + 1, q) + rng.normal(0, 1, q) * 2.0 ** rng.uniform(-24, -8, q)) / nmu, 0, 1)
+    perp = np.cross(u[-q:], v[-q:]); perp /= np.linalg.norm(perp, axis=1)[:, None]
+    xa = x1[-q:].astype(np.float64)
+    xb = x2[-q:].copy()
+    for _ in range(10):
+        h = xa + xb; h /= np.linalg.norm(h, axis=1)[:, None]
+        e2 = perp - (perp * h).sum(1)[:, None] * h; e2 /= np.linalg.norm(e2, axis=1)[:, None]
+        xb = xa + sep[-q:, None] * (mu_t[:, None] * h + np.sqrt(1 - mu_t ** 2)[:, None] * e2)
+    x2[-q:] = xb
+    x2 = x2.astype(real)
+    s1 = ((x1[:, 0] * x1[:, 0] + x1[:, 1] * x1[:, 1]) + x1[:, 2] * x1[:, 2]).astype(real)
+    s2 = ((x2[:, 0] * x2[:, 0] + x2[:, 1] * x2[:, 1]) + x2[:, 2] * x2[:, 2]).astype(real)
+    t = (real(2) * ((x1[:, 0] * x2[:, 0] + x1[:, 1] * x2[:, 1]) + x1[:, 2] * x2[:, 2])).astype(real)
+    d2, es, em = survey_exact(t, s1, s2, ns, nmu, arith, real)
+    keep = (d2 < real(ns * ns)) & (d2 >= 0)                   # what the range test lets through
+    uniform = ((np.arange(n) >= k) & (np.arange(n) < n - q))[keep]       # the pairs that were not planted next to a bin edge
+    t, s1, s2, es, em = t[keep], s1[keep], s2[keep], es[keep], em[keep]
+    m = len(t)
+    e = 2.0 ** -22
+    for d1, dd2 in ((rng.uniform(-e, e, m), rng.uniform(-e, e, m)), (e, e), (-e, -e), (e, -e), (-e, e)):
+        fs, fm, flagged = survey_fast(t, s1, s2, ns, nmu, ks, km, d1, dd2)
+        clean = ~flagged
+        assert np.array_equal(fs[clean], es[clean]), "an unflagged pair got a different s bin"
+        assert np.array_equal(fm[clean], em[clean]), "an unflagged pair got a different mu bin"
+    assert flagged[uniform].mean() < 0.02                     # the band is narrow on ordinary pairs
