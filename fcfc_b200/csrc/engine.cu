@@ -33,6 +33,25 @@ extern "C" void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, 
   if (km) *km = pick(2.2 * (periodic ? 4.5e-7 : 9.5e-7) * (nmu + 1), nmu);
 }
 
+// Limits of the division-free pre-tests of the survey (s_perp, pi) metric (count_kernel.cuh, eval_pair), each rounded
+// up to the build's `real`: out[0] the sphere s^2 < (s2max + p2max)(1 + 8 eps) searched before anything else;
+// out[1] p2max (1 + 8 eps) for d*d < (s + t) p2max'; out[2] c = s2max (1 + 32 eps) + 32 eps out[0] for
+// (s^2 - c)(s + t) < d*d: c >= s2max (1 + 2 eps) + 3.2 eps max(s^2) keeps it a necessary condition of the exact test
+// through every rounding (derivation in DESIGN.md), padded tenfold.  Exported for tests/test_fastbin_budget.py.
+extern "C" void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int is_float, double out[3]) {
+  const double eps = is_float ? (double) FLT_EPSILON : DBL_EPSILON;
+  auto up = [&](double v) {
+    if (!is_float) return v;
+    float f = (float) v;
+    if ((double) f < v) f = std::nextafter(f, INFINITY);
+    return (double) f;
+  };
+  const double pm = (s2max + p2max) * (1 + 8 * eps);
+  out[0] = up(pm);
+  out[1] = up(p2max * (1 + 8 * eps));
+  out[2] = up(s2max * (1 + 32 * eps) + 32 * eps * pm);
+}
+
 namespace fcfc {
 
 // ------------------------------------------------------------------------------------------
@@ -680,16 +699,10 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   P.rows = reinterpret_cast<const int4 *>(dbuf + o_rows); P.nrows = (int) rows.size();
   P.s2min = (T) s2min; P.s2max = (T) s2max; P.pmin = (T) pmin; P.pmax = (T) pmax;
   {
-    // survey (s_perp, pi): cheap pre-test s^2 < s2max + p2max before the division (see eval_pair)
-    double pm = (s2max + pmax) * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
-    P.premax = (T) pm; if ((double) P.premax < pm) P.premax = std::nextafter(P.premax, (T) INFINITY);
-    const double pp = pmax * (1 + 8 * (is_float ? (double) FLT_EPSILON : DBL_EPSILON));
-    P.pmax_pre = (T) pp; if ((double) P.pmax_pre < pp) P.pmax_pre = std::nextafter(P.pmax_pre, (T) INFINITY);
-    // s_perp^2 pre-test (s^2 - c)(s + t) < d*d: c >= s2max (1 + 2 eps) + 3.2 eps max(s^2) keeps it a necessary
-    // condition of the exact test through every rounding (derivation in DESIGN.md); padded tenfold
-    const double eps = is_float ? (double) FLT_EPSILON : DBL_EPSILON;
-    const double sp = s2max * (1 + 32 * eps) + 32 * eps * pm;
-    P.s2max_pre = (T) sp; if ((double) P.s2max_pre < sp) P.s2max_pre = std::nextafter(P.s2max_pre, (T) INFINITY);
+    // survey (s_perp, pi): limits of the division-free pre-tests of eval_pair, already rounded up to `real`
+    double lim[3];
+    fcfc_gpu_survey_pretest_limits(s2max, pmax, is_float ? 1 : 0, lim);
+    P.premax = (T) lim[0]; P.pmax_pre = (T) lim[1]; P.s2max_pre = (T) lim[2];
   }
   P.nmu2 = nmu * nmu; P.nmu2f = (T) (nmu * nmu);
   P.ns = ns; P.np = np; P.ntot = (int) ntot;

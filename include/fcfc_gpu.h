@@ -164,6 +164,9 @@ double fcfc_gpu_measure_fp64_peak(void);
 /* Diagnostics: the fixed-point scales 2^ks, 2^km the counting kernels use for their computed s and mu bins
  * (host arithmetic only; the CPU tests check the error budget behind them). */
 void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km);
+/* Diagnostics: limits of the division-free pre-tests of the survey (s_perp, pi) metric, rounded up to the build's
+ * real type: out[0] searched sphere, out[1] padded p2max, out[2] padded s2max. */
+void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int is_float, double out[3]);
 
 #ifdef __cplusplus
 }

@@ -186,3 +186,53 @@ def test_survey_unflagged_pairs_are_binned_exactly(ns, nmu, arith, real):
         assert np.array_equal(fs[clean], es[clean]), "an unflagged pair got a different s bin"
         assert np.array_equal(fm[clean], em[clean]), "an unflagged pair got a different mu bin"
     assert flagged[uniform].mean() < 0.02                     # the band is narrow on ordinary pairs
+
+
+# ---------------------------------------------------------------------------------------------------
+# Survey (s_perp, pi): the pair loop keeps a candidate off the stacks with two division-free tests
+# (count_kernel.cuh, eval_pair); the exact tests, with the division, run later (finish_pair).  Bit-exactness needs
+# the cheap tests to be NECESSARY conditions of the exact ones through every rounding.
+@pytest.mark.parametrize("real", [np.float32, np.float64])
+@pytest.mark.parametrize("smax,pimax", [(40.0, 80.0), (10.0, 100.0), (150.0, 20.0)])
+def test_survey_spi_pretests_never_drop_an_accepted_pair(real, smax, pimax):
+    L = F.lib()
+    lim = (ctypes.c_double * 3)()
+    s2max, p2max = smax * smax, pimax * pimax                # the survey metric bins pi^2 (count_func.c:5296)
+    L.fcfc_gpu_survey_pretest_limits(ctypes.c_double(s2max), ctypes.c_double(p2max), int(real is np.float32), lim)
+    premax, pmax_pre, s2max_pre = (real(v) for v in lim)
+    assert float(premax) >= s2max + p2max and float(pmax_pre) >= p2max and float(s2max_pre) >= s2max
+    rng = np.random.default_rng(int(smax) * 7 + int(pimax))
+    n = 1_500_000
+    r1 = rng.uniform(200.0, 340.0, n)
+    # separations in cylinder coordinates about the line of sight; two thirds planted on the cylinder's surfaces
+    sperp = np.sqrt(rng.uniform(0, 1.2 * s2max, n))
+    pi = rng.uniform(0, 1.2 * pimax, n)
+    k = n // 3
+    sperp[:k] = smax * (1 + rng.normal(0, 1, k) * 2.0 ** rng.uniform(-40, -12, k))
+    pi[k:2 * k] = pimax * (1 + rng.normal(0, 1, k) * 2.0 ** rng.uniform(-40, -12, k))
+    u = rng.normal(size=(n, 3)); u /= np.linalg.norm(u, axis=1)[:, None]
+    w = rng.normal(size=(n, 3)); w -= (w * u).sum(1)[:, None] * u; w /= np.linalg.norm(w, axis=1)[:, None]
+    xa = u * r1[:, None]
+    xb = xa + pi[:, None] * u + sperp[:, None] * w
+    for _ in range(8):                                       # the line of sight is along x1 + x2
+        h = xa + xb; h /= np.linalg.norm(h, axis=1)[:, None]
+        e2 = w - (w * h).sum(1)[:, None] * h; e2 /= np.linalg.norm(e2, axis=1)[:, None]
+        xb = xa + pi[:, None] * h + sperp[:, None] * e2
+    x1, x2 = xa.astype(real), xb.astype(real)
+    s1 = ((x1[:, 0] * x1[:, 0] + x1[:, 1] * x1[:, 1]) + x1[:, 2] * x1[:, 2]).astype(real)
+    s2 = ((x2[:, 0] * x2[:, 0] + x2[:, 1] * x2[:, 1]) + x2[:, 2] * x2[:, 2]).astype(real)
+    t = (real(2) * ((x1[:, 0] * x2[:, 0] + x1[:, 1] * x2[:, 1]) + x1[:, 2] * x2[:, 2])).astype(real)
+    # exact path (2pt/metric_common.c:169-205; finish_pair)
+    s = s1 + s2
+    d2 = s - t
+    d = s1 - s2
+    st = s + t
+    dd = d * d
+    num = dd / st
+    accepted = (num < real(p2max)) & ((d2 - num) < real(s2max))
+    # cheap path (eval_pair)
+    ok = (d2 < premax) & (dd < st * pmax_pre) & ((d2 - s2max_pre) * st < dd)
+    assert accepted.sum() > n // 10 and (~accepted).sum() > n // 10
+    assert not np.any(accepted & ~ok), "a pre-test dropped a pair the exact tests accept"
+    # and they are sharp: nearly everything they let through is accepted
+    assert (ok & ~accepted).sum() < 0.02 * ok.sum() + 2 * k * 0.6
