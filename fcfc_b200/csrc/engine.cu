@@ -513,6 +513,26 @@ static std::vector<int2> stencil_inside(const Grid &g, const std::vector<int4> &
   return in;
 }
 
+}  // namespace fcfc
+// Diagnostics for the CPU tests (tests/test_stencil.py): the neighbour stencil and its dense sub-ranges for cells of size
+// cs[3], a spherical reach r2 (squared) and the maximum separation s2max, exactly as the counting path builds them.
+// rows_out[4 i .. 4 i + 3] = (dx, dy, dz_lo, dz_hi), inside_out[2 i .. 2 i + 1] = (dz_lo, dz_hi) of the dense cells
+// ((1, 0) = none).  Returns the number of rows (nothing is written beyond max_rows).
+extern "C" int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2max, int half, int *rows_out, int *inside_out, int max_rows) {
+  fcfc::Grid g;
+  for (int d = 0; d < 3; d++) g.cs[d] = cs[d];
+  fcfc::Reach R;
+  R.cylinder = false; R.r2 = r2; R.r2_xy = r2; R.r_z = std::sqrt(r2);
+  const std::vector<int4> rows = fcfc::build_stencil(g, R, half != 0);
+  const std::vector<int2> in = fcfc::stencil_inside(g, rows, s2max);
+  for (size_t i = 0; i < rows.size() && (int) i < max_rows; i++) {
+    rows_out[4 * i] = rows[i].x; rows_out[4 * i + 1] = rows[i].y; rows_out[4 * i + 2] = rows[i].z; rows_out[4 * i + 3] = rows[i].w;
+    inside_out[2 * i] = in[i].x; inside_out[2 * i + 1] = in[i].y;
+  }
+  return (int) rows.size();
+}
+namespace fcfc {
+
 static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[3], const double hi[3],
                         double n1, double n2, int tile, bool half) {
   Grid best; double best_cost = 1e300;

@@ -167,6 +167,9 @@ void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km);
 /* Diagnostics: limits of the division-free pre-tests of the survey (s_perp, pi) metric, rounded up to the build's
  * real type: out[0] searched sphere, out[1] padded p2max, out[2] padded s2max. */
 void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int is_float, double out[3]);
+/* Diagnostics: the neighbour-cell stencil (rows (dx, dy, dz_lo, dz_hi)) and the dense sub-range of every row for cells
+ * of size cs[3], a spherical reach r2 (squared) and the maximum separation s2max (squared); returns the row count. */
+int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2max, int half, int *rows_out, int *inside_out, int max_rows);
 
 #ifdef __cplusplus
 }
