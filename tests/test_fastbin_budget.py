@@ -236,3 +236,33 @@ def test_survey_spi_pretests_never_drop_an_accepted_pair(real, smax, pimax):
     assert not np.any(accepted & ~ok), "a pre-test dropped a pair the exact tests accept"
     # and they are sharp: nearly everything they let through is accepted
     assert (ok & ~accepted).sum() < 0.02 * ok.sum() + 2 * k * 0.6
+
+
+# ---------------------------------------------------------------------------------------------------
+# Two small lemmas the exact re-binning path relies on (count_kernel.cuh: isqrt_small, div_rz_pos).
+def test_isqrt_from_an_approximate_square_root_exhaustive():
+    """floor(sqrt(m)) == trunc(sqrt.approx(m + 1/2)) for every integer 0 <= m < 2^18, whatever the sign of the
+    approximation's error (2^-22 relative is far more than sqrt.approx.ftz.f32 is off)."""
+    m = np.arange(1 << 18, dtype=np.int64)
+    want = np.floor(np.sqrt(m.astype(np.float64))).astype(np.int64)
+    arg = (m.astype(f32) + f32(0.5)).astype(np.float64)      # exact in float32 for m < 2^23
+    for delta in (0.0, 2.0 ** -22, -(2.0 ** -22)):
+        approx = (np.sqrt(arg) * (1.0 + delta)).astype(f32)
+        assert np.array_equal(np.trunc(approx).astype(np.int64), want)
+
+
+def test_round_toward_zero_quotient_from_the_rounded_one():
+    """div_rz_pos: q = RN(a / b), one ulp down when the exact residual a - q b is negative, equals RZ(a / b)."""
+    rng = np.random.default_rng(11)
+    n = 2_000_000
+    a = (rng.random(n) * 2.0 ** rng.integers(-10, 20, n)).astype(f32)
+    b = (rng.random(n) * 2.0 ** rng.integers(-10, 20, n) + 1e-6).astype(f32)
+    a[: n // 4] = (b[: n // 4].astype(np.float64) * rng.integers(1, 4000, n // 4)).astype(f32)      # (nearly) exact quotients
+    q = (a / b).astype(f32)
+    resid = a.astype(np.float64) - q.astype(np.float64) * b.astype(np.float64)      # 24 x 24 bits: exact in float64
+    got = np.where(resid < 0, np.nextafter(q, f32(0)), q)
+    # reference: the quotient in extended precision, truncated to 24 bits
+    ql = a.astype(np.longdouble) / b.astype(np.longdouble)
+    want = ql.astype(f32)
+    want = np.where(want.astype(np.longdouble) > ql, np.nextafter(want, f32(0)), want)
+    assert np.array_equal(got, want)
