@@ -83,6 +83,7 @@ def lib():
         L.fcfc_gpu_measure_fp64_peak.restype = C.c_double
         L.fcfc_gpu_measure_fp64_peak.argtypes = []
         L.fcfc_gpu_init.argtypes = [C.c_int, C.c_void_p, C.c_int]
+        L.fcfc_gpu_set_option.argtypes = [C.c_char_p, C.c_long]
         _lib = L
     return _lib
 
@@ -102,6 +103,12 @@ def init(devices=None, verbose: int = 0) -> int:
     if n <= 0:
         raise FcfcGpuError(last_error(), n)
     return n
+
+
+def set_option(name: str, value: int = 1) -> None:
+    """Tuning / diagnostic switch of the engine (include/fcfc_gpu.h: fcfc_gpu_set_option); "defaults" resets all."""
+    if lib().fcfc_gpu_set_option(name.encode(), int(value)) != 0:
+        raise FcfcGpuError(last_error(), -2)
 
 
 def n_linear_bins(lo: float, hi: float, step: float) -> int:

@@ -33,6 +33,16 @@
 #include <stdint.h>
 #include <float.h>
 
+// Shared-memory loads written as inline PTX are volatile (see the note above QOps); 0 restores plain asm for A/B builds.
+#ifndef FCFC_LDS_VOLATILE
+#define FCFC_LDS_VOLATILE 1
+#endif
+#if FCFC_LDS_VOLATILE
+#define FCFC_LDS_ASM asm volatile
+#else
+#define FCFC_LDS_ASM asm
+#endif
+
 namespace fcfc {
 
 enum { BIN_ISO = 0, BIN_SMU = 1, BIN_SPI = 2 };
@@ -305,6 +315,12 @@ __device__ __forceinline__ void sweep_hist(unsigned int *h, unsigned long long *
 
 // ---------------------------------------------------------------------------------------------
 // Per-lane stacks of accepted pairs, addressed with 32-bit shared-window addresses.
+// Every shared-memory access written as inline PTX in this file is `asm volatile`: to the compiler a plain asm is a pure
+// function of its operands, and a load whose address register holds the same value in every chunk could legally be
+// merged with an earlier one across the stores that refill the buffer.  Volatile asms keep their order among
+// themselves and against __syncwarp() (itself a volatile asm with a memory clobber, which also orders the ordinary
+// C++ stores of the staging code), and that is all the ordering these buffers need; a "memory" clobber on the loads
+// would in addition make the compiler re-read kernel parameters from the constant bank inside the pair loops.
 // Layout: [slot][lane][NW words]; a warp-wide push or pop touches 32 consecutive entries (no bank conflicts).
 template <class T, int NW> struct QOps;
 // push: predicated store + predicated pointer bump in one asm block (a stack: no wrap-around arithmetic)
@@ -318,9 +334,9 @@ template <int NW> struct QOps<float, NW> {
     else asm volatile(FCFC_PUSH_ASM("@q st.shared.v4.f32 [%0], {%3, %4, %5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "f"(v[0]), "f"(v[1 % NW]), "f"(v[2 % NW]), "f"(v[3 % NW]));
   }
   static __device__ __forceinline__ void load(unsigned a, float (&v)[NW]) {
-    if (NW == 1) asm("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a));
-    else if (NW == 2) asm("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1 % NW]) : "r"(a));
-    else asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1 % NW]), "=f"(v[2 % NW]), "=f"(v[3 % NW]) : "r"(a));
+    if (NW == 1) FCFC_LDS_ASM("ld.shared.f32 %0, [%1];" : "=f"(v[0]) : "r"(a));
+    else if (NW == 2) FCFC_LDS_ASM("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(v[0]), "=f"(v[1 % NW]) : "r"(a));
+    else FCFC_LDS_ASM("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v[0]), "=f"(v[1 % NW]), "=f"(v[2 % NW]), "=f"(v[3 % NW]) : "r"(a));
   }
 };
 template <int NW> struct QOps<double, NW> {
@@ -332,10 +348,10 @@ template <int NW> struct QOps<double, NW> {
     else asm volatile(FCFC_PUSH_ASM("@q st.shared.v2.f64 [%0], {%3, %4}; @q st.shared.v2.f64 [%0+16], {%5, %6};") : "+r"(w) : "r"((int) p), "n"(S), "d"(v[0]), "d"(v[1 % NW]), "d"(v[2 % NW]), "d"(v[3 % NW]));
   }
   static __device__ __forceinline__ void load(unsigned a, double (&v)[NW]) {
-    if (NW == 1) asm("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a));
+    if (NW == 1) FCFC_LDS_ASM("ld.shared.f64 %0, [%1];" : "=d"(v[0]) : "r"(a));
     else {
-      asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1 % NW]) : "r"(a));
-      if (NW == 4) asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v[2 % NW]), "=d"(v[3 % NW]) : "r"(a));
+      FCFC_LDS_ASM("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v[0]), "=d"(v[1 % NW]) : "r"(a));
+      if (NW == 4) FCFC_LDS_ASM("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(v[2 % NW]), "=d"(v[3 % NW]) : "r"(a));
     }
   }
 };
@@ -663,11 +679,11 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
 }
 
 __device__ __forceinline__ void lds_vec4_raw(unsigned a, float &x, float &y, float &z, float &w) {
-  asm("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
+  FCFC_LDS_ASM("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(x), "=f"(y), "=f"(z), "=f"(w) : "r"(a));
 }
 __device__ __forceinline__ void lds_vec4_raw(unsigned a, double &x, double &y, double &z, double &w) {
-  asm("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
-  asm("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(z), "=d"(w) : "r"(a));
+  FCFC_LDS_ASM("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(x), "=d"(y) : "r"(a));
+  FCFC_LDS_ASM("ld.shared.v2.f64 {%0, %1}, [%2+16];" : "=d"(z), "=d"(w) : "r"(a));
 }
 template <class T> __device__ __forceinline__ Vec4<T> lds_vec4(unsigned a) { Vec4<T> v; lds_vec4_raw(a, v.x, v.y, v.z, v.s); return v; }
 
@@ -770,8 +786,8 @@ __device__ __forceinline__ int do_chunk_dense(const CountParams<T> &P, LaneQueue
   for (; sa != se; sa += 32u) {
     if (__any_sync(0xffffffffu, Q.top > lim)) break;
     f32x2 X, Y, Z;
-    asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
-    asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
+    FCFC_LDS_ASM("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
+    FCFC_LDS_ASM("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
     float zz[2];
     upk2(Z, zz[0], zz[1]);
 #pragma unroll
@@ -823,8 +839,8 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
     for (; sa != se; sa += 32u) {
       if (__any_sync(0xffffffffu, Q.top > lim)) break;
       f32x2 X, Y, Z;
-      asm("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
-      asm("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
+      FCFC_LDS_ASM("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
+      FCFC_LDS_ASM("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
       float zz[2];
       upk2(Z, zz[0], zz[1]);
 #pragma unroll
@@ -860,9 +876,9 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
     Vec4<T> b;
     if constexpr (kPacked) {      // (only the tile against its own points gets here: SELF) pair layout, one point
       const unsigned int pa = staged_pair_addr(sbuf_s, j);
-      asm("ld.shared.f32 %0, [%1];" : "=f"(b.x) : "r"(pa));
-      asm("ld.shared.f32 %0, [%1+8];" : "=f"(b.y) : "r"(pa));
-      asm("ld.shared.f32 %0, [%1+16];" : "=f"(b.z) : "r"(pa));
+      FCFC_LDS_ASM("ld.shared.f32 %0, [%1];" : "=f"(b.x) : "r"(pa));
+      FCFC_LDS_ASM("ld.shared.f32 %0, [%1+8];" : "=f"(b.y) : "r"(pa));
+      FCFC_LDS_ASM("ld.shared.f32 %0, [%1+16];" : "=f"(b.z) : "r"(pa));
       b.s = 0;
     } else b = lds_vec4<T>(sa);
     T bw = (T) 1;

@@ -72,6 +72,60 @@ static void set_err(const char *fmt, ...) {
     cudaGetLastError(); return code; } } while (0)
 
 // ------------------------------------------------------------------------------------------
+// Tuning / diagnostic options.  They are NOT read from the environment on the counting path: the process-wide
+// defaults are parsed once by fcfc_gpu_init from FCFC_GPU_TUNE="name=value,..." and can be changed explicitly
+// with fcfc_gpu_set_option (tests, A/B scripts).  Every count call works on a snapshot taken at its entry.
+struct Options {
+  int k = 0;                // force cells of reach / k (0: cost model of choose_grid)
+  int nsplit = 0;           // force the number of pieces every tile's sweep list is cut into (0: automatic)
+  int items_per_warp = 8;   // automatic nsplit: work items per resident warp and shard
+  int cost_bits = 1;        // mantissa bits of the cost classes of the work-item order (23: exact cost order)
+  int no_subsort = 0;       // 1: no Morton order inside the cells
+  int no_table_math = 0;    // 1: always look the bins up, never compute them
+  int no_hist_copies = 0;   // 1: one weighted shared-memory histogram instead of 32 lane-private copies
+  int qdepth = 0;           // cap of the per-lane stack depth (0: as deep as shared memory allows, <= 64)
+  int qkeep = -1;           // entries a drain leaves on the fullest stack (-1: automatic)
+  int force_generic = 0;    // 1: run the generic variant (cross-check of the fast paths)
+  int global_hist = 0;      // 1: histogram in global memory
+  int no_dense = 0;         // 1: dense-cell path off
+  int no_prefilter = 0;     // 1: double-precision kernels without the float pre-filter
+  int sorted_copies = 3;    // cell-sorted copies kept per catalogue and precision (one per grid in use)
+};
+static Options g_opt;
+static std::mutex g_opt_mutex;
+
+static int set_option(const char *name, long value) {
+  if (!name) return FCFC_GPU_ERR_ARG;
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  const struct { const char *n; int *p; } tab[] = {
+      {"k", &g_opt.k}, {"nsplit", &g_opt.nsplit}, {"items_per_warp", &g_opt.items_per_warp}, {"cost_bits", &g_opt.cost_bits},
+      {"no_subsort", &g_opt.no_subsort}, {"no_table_math", &g_opt.no_table_math}, {"no_hist_copies", &g_opt.no_hist_copies},
+      {"qdepth", &g_opt.qdepth}, {"qkeep", &g_opt.qkeep}, {"force_generic", &g_opt.force_generic},
+      {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter},
+      {"sorted_copies", &g_opt.sorted_copies}};
+  if (!strcmp(name, "defaults")) { g_opt = Options(); return 0; }
+  for (auto &t : tab) if (!strcmp(name, t.n)) { *t.p = (int) value; return 0; }
+  return FCFC_GPU_ERR_ARG;
+}
+static Options options_snapshot() { std::lock_guard<std::mutex> lock(g_opt_mutex); return g_opt; }
+// FCFC_GPU_TUNE="k=3,no_dense=1": parsed once, by fcfc_gpu_init
+static void options_from_env() {
+  const char *e = getenv("FCFC_GPU_TUNE");
+  if (!e) return;
+  std::string s(e);
+  size_t pos = 0;
+  while (pos < s.size()) {
+    size_t end = s.find(',', pos); if (end == std::string::npos) end = s.size();
+    const std::string item = s.substr(pos, end - pos);
+    const size_t eq = item.find('=');
+    const std::string key = item.substr(0, eq);
+    const long val = (eq == std::string::npos) ? 1 : atol(item.c_str() + eq + 1);
+    if (!key.empty() && set_option(key.c_str(), val) != 0) fprintf(stderr, "[fcfc_gpu] FCFC_GPU_TUNE: unknown option '%s' ignored\n", key.c_str());
+    pos = end + 1;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // device context (one per process; multi-GPU jobs run one process per GPU, or list several
 // devices here and let fcfc_gpu_count loop over them)
 struct Context {
@@ -146,6 +200,30 @@ static void pool_release_all() {
 }
 template <class P> static cudaError_t pool_alloc(P **out, size_t bytes) { return pool_alloc(reinterpret_cast<void **>(out), bytes); }
 
+// Scope guards: pool blocks and events are released on every exit path of a call.
+struct PoolScope {
+  std::vector<void *> held;
+  template <class P> cudaError_t alloc(P **out, size_t bytes) {
+    cudaError_t e = pool_alloc(out, bytes);
+    if (e == cudaSuccess) held.push_back(*out);
+    return e;
+  }
+  void free_now(void *p) {            // early release of one block
+    for (size_t i = 0; i < held.size(); i++) if (held[i] == p) { held.erase(held.begin() + i); pool_free(p); return; }
+  }
+  template <class P> P *keep(P *p) {  // ownership passes to the caller
+    for (size_t i = 0; i < held.size(); i++) if (held[i] == p) { held.erase(held.begin() + i); break; }
+    return p;
+  }
+  ~PoolScope() { for (void *p : held) pool_free(p); }
+};
+struct EventScope {
+  std::vector<cudaEvent_t> ev;
+  explicit EventScope(int n) : ev(n) { for (auto &e : ev) cudaEventCreate(&e); }
+  cudaEvent_t operator[](int i) const { return ev[i]; }
+  ~EventScope() { for (auto &e : ev) cudaEventDestroy(e); }
+};
+
 // ------------------------------------------------------------------------------------------
 // cell grid
 struct Grid {
@@ -163,6 +241,7 @@ struct Grid {
 
 template <class T> struct Sorted {
   bool valid = false;
+  unsigned long long stamp = 0; // last use (the least recently used copy is evicted)
   Grid grid;
   int tile = 0;                 // points per work item
   Vec4<T> *pos = nullptr;
@@ -189,8 +268,11 @@ struct DevCat {
   double bmin[3], bmax[3];      // bounding box of the (rescaled) coordinates
   double smax = 0;              // max of x^2+y^2+z^2
   double wsum = 0;
-  fcfc::Sorted<float> sf;
-  fcfc::Sorted<double> sd;
+  // cell-sorted copies, one per (grid, tile) in use: DD, DR and RR of a survey run on different grids (the grid
+  // follows the extents and sizes of both catalogues), and each keeps its copy instead of re-sorting on every call
+  std::vector<fcfc::Sorted<float>> sf;
+  std::vector<fcfc::Sorted<double>> sd;
+  unsigned long long clock = 0;
 };
 
 // The public handle: one replica per device in use (the secondary catalogue must be resident everywhere).
@@ -204,9 +286,9 @@ struct fcfc_gpu_catalog {
 
 namespace fcfc {
 
-template <class T> static Sorted<T> &sorted_of(DevCat *c);
-template <> Sorted<float> &sorted_of<float>(DevCat *c) { return c->sf; }
-template <> Sorted<double> &sorted_of<double>(DevCat *c) { return c->sd; }
+template <class T> static std::vector<Sorted<T>> &sorted_of(DevCat *c);
+template <> std::vector<Sorted<float>> &sorted_of<float>(DevCat *c) { return c->sf; }
+template <> std::vector<Sorted<double>> &sorted_of<double>(DevCat *c) { return c->sd; }
 
 // ------------------------------------------------------------------------------------------
 // catalogue kernels
@@ -272,7 +354,9 @@ __global__ void cellid_kernel(const T *x, const T *y, const T *z, int n, Grid g,
   for (int k = 0; k < 3; k++) {
     double u = (p[k] - g.origin[k]) / g.cs[k];
     int ci = (int) floor(u);
-    if (g.periodic && !(p[k] >= 0 && p[k] <= g.box[k])) atomicExch(err, 1);   // x == L happens after rounding to float
+    // one period of the box, wherever it starts (the reference never range-checks: only differences and +-L shifts enter
+    // the metric, so a box stored as [-L/2, L/2] is as good as [0, L]); x == origin + L happens after rounding to float
+    if (g.periodic && !(p[k] >= g.origin[k] && p[k] <= g.origin[k] + g.box[k])) atomicExch(err, 1);
     c[k] = min(max(ci, 0), g.nc[k] - 1);
     q[k] = (unsigned int) min(max((int) ((u - c[k]) * 4.0), 0), 3);
   }
@@ -369,34 +453,45 @@ __global__ void item_cost_kernel(const int *item_cell, const int *item_cnt, int 
 }
 
 // ------------------------------------------------------------------------------------------
+// The cell-sorted copy of a catalogue for grid g (built on first use, then kept: see DevCat).
 template <class T>
-static int build_sorted(DevCat *cat, const Grid &g, int tile, bool need_w, float *ms_out) {
-  Sorted<T> &S = sorted_of<T>(cat);
-  if (S.valid && S.grid == g && S.tile == tile && (!need_w || S.w)) return 0;
-  S.release();
+static int build_sorted(DevCat *cat, const Grid &g, int tile, bool need_w, const Options &opt, float *ms_out, Sorted<T> **out) {
+  std::vector<Sorted<T>> &all = sorted_of<T>(cat);
+  for (auto &S : all)
+    if (S.valid && S.grid == g && S.tile == tile && (!need_w || S.w)) { S.stamp = ++cat->clock; *out = &S; return 0; }
+  // evict the least recently used copies beyond the cap (and stale ones without weights for this grid)
+  for (size_t i = 0; i < all.size();)
+    if (!all[i].valid || (all[i].grid == g && all[i].tile == tile)) { all[i].release(); all.erase(all.begin() + i); } else i++;
+  while ((int) all.size() >= std::max(1, opt.sorted_copies)) {
+    size_t lru = 0;
+    for (size_t i = 1; i < all.size(); i++) if (all[i].stamp < all[lru].stamp) lru = i;
+    all[lru].release(); all.erase(all.begin() + lru);
+  }
+  Sorted<T> S;
   const int n = (int) cat->n;
   const long long ncell = g.ncell();
-  cudaEvent_t e0, e1; cudaEventCreate(&e0); cudaEventCreate(&e1); cudaEventRecord(e0);
+  EventScope ev(2);
+  PoolScope pool;
+  cudaEventRecord(ev[0]);
   unsigned int *key = nullptr, *key2 = nullptr; int *idx = nullptr, *idx2 = nullptr, *err = nullptr;
   int *ntile = nullptr, *tile_off = nullptr; void *tmp = nullptr;
-  auto cleanup = [&]() { pool_free(key); pool_free(key2); pool_free(idx); pool_free(idx2); pool_free(err); pool_free(ntile); pool_free(tile_off); pool_free(tmp); };
-#define TRY_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err("%s: %s", #x, cudaGetErrorString(e_)); cudaGetLastError(); cleanup(); S.release(); return FCFC_GPU_ERR_TREE; } } while (0)
+#define TRY_(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { set_err("%s: %s", #x, cudaGetErrorString(e_)); cudaGetLastError(); return FCFC_GPU_ERR_TREE; } } while (0)
   const size_t nn = n ? n : 1;
-  TRY_(pool_alloc(&key, nn * 4)); TRY_(pool_alloc(&key2, nn * 4)); TRY_(pool_alloc(&idx, nn * 4)); TRY_(pool_alloc(&idx2, nn * 4));
-  TRY_(pool_alloc(&err, 4)); TRY_(cudaMemset(err, 0, 4));
-  TRY_(pool_alloc(&S.pos, nn * sizeof(Vec4<T>)));
-  if (need_w) TRY_(pool_alloc(&S.w, nn * sizeof(T)));
-  TRY_(pool_alloc(&S.cell_start, (ncell + 1) * sizeof(int)));
+  TRY_(pool.alloc(&key, nn * 4)); TRY_(pool.alloc(&key2, nn * 4)); TRY_(pool.alloc(&idx, nn * 4)); TRY_(pool.alloc(&idx2, nn * 4));
+  TRY_(pool.alloc(&err, 4)); TRY_(cudaMemset(err, 0, 4));
+  TRY_(pool.alloc(&S.pos, nn * sizeof(Vec4<T>)));
+  if (need_w) TRY_(pool.alloc(&S.w, nn * sizeof(T)));
+  TRY_(pool.alloc(&S.cell_start, (ncell + 1) * sizeof(int)));
   const int nb = (n + 255) / 256;
   int bits = 1; while ((1ll << bits) < ncell) bits++;
-  const int sub = getenv("FCFC_GPU_NO_SUBSORT") ? 0 : std::min(6, 31 - bits);   // Morton bits inside the cell
+  const int sub = opt.no_subsort ? 0 : std::min(6, 31 - bits);   // Morton bits inside the cell
   if (n) {
     cellid_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z, n, g, sub, key, idx, err);
     g_stats.kernel_launches++;
     bits += sub;
     size_t tb = 0;
     TRY_(cub::DeviceRadixSort::SortPairs(nullptr, tb, key, key2, idx, idx2, n, 0, bits));
-    TRY_(pool_alloc(&tmp, tb ? tb : 1));
+    TRY_(pool.alloc(&tmp, tb ? tb : 1));
     TRY_(cub::DeviceRadixSort::SortPairs(tmp, tb, key, key2, idx, idx2, n, 0, bits));
     gather_kernel<T><<<nb, 256>>>((const T *) cat->x, (const T *) cat->y, (const T *) cat->z,
                                   cat->has_s ? (const T *) cat->s : nullptr, cat->has_w ? (const T *) cat->w : nullptr,
@@ -408,32 +503,34 @@ static int build_sorted(DevCat *cat, const Grid &g, int tile, bool need_w, float
   int herr = 0;
   TRY_(cudaMemcpy(&herr, err, 4, cudaMemcpyDeviceToHost));
   if (herr) {
-    set_err("catalogue has points outside the periodic box: FCFC_2PT_BOX expects 0 <= x <= BOX_SIZE");
-    cleanup(); S.release(); return FCFC_GPU_ERR_DATA;
+    set_err("catalogue has points outside one period of the box: FCFC_2PT_BOX expects max - min <= BOX_SIZE on every axis");
+    return FCFC_GPU_ERR_DATA;
   }
   // work items
-  TRY_(pool_alloc(&ntile, (ncell + 1) * sizeof(int))); TRY_(pool_alloc(&tile_off, (ncell + 1) * sizeof(int)));
+  TRY_(pool.alloc(&ntile, (ncell + 1) * sizeof(int))); TRY_(pool.alloc(&tile_off, (ncell + 1) * sizeof(int)));
   TRY_(cudaMemset(ntile, 0, (ncell + 1) * sizeof(int)));
   ntile_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, (int) ncell, tile, ntile);
-  pool_free(tmp); tmp = nullptr;
+  pool.free_now(tmp); tmp = nullptr;
   size_t tb = 0;
   TRY_(cub::DeviceScan::ExclusiveSum(nullptr, tb, ntile, tile_off, (int) ncell + 1));
-  TRY_(pool_alloc(&tmp, tb ? tb : 1));
+  TRY_(pool.alloc(&tmp, tb ? tb : 1));
   TRY_(cub::DeviceScan::ExclusiveSum(tmp, tb, ntile, tile_off, (int) ncell + 1));
   int nitem = 0;
   TRY_(cudaMemcpy(&nitem, tile_off + ncell, 4, cudaMemcpyDeviceToHost));
   S.nitem = nitem;
   const size_t ni = nitem ? nitem : 1;
-  TRY_(pool_alloc(&S.item_cell, ni * 4)); TRY_(pool_alloc(&S.item_off, ni * 4)); TRY_(pool_alloc(&S.item_cnt, ni * 4));
+  TRY_(pool.alloc(&S.item_cell, ni * 4)); TRY_(pool.alloc(&S.item_off, ni * 4)); TRY_(pool.alloc(&S.item_cnt, ni * 4));
   items_kernel<<<(int) ((ncell + 255) / 256), 256>>>(S.cell_start, tile_off, (int) ncell, tile, S.item_cell, S.item_off, S.item_cnt);
   g_stats.kernel_launches += 3;
   TRY_(cudaGetLastError());
-  cudaEventRecord(e1); TRY_(cudaEventSynchronize(e1));
-  float ms = 0; cudaEventElapsedTime(&ms, e0, e1); if (ms_out) *ms_out += ms;
-  cudaEventDestroy(e0); cudaEventDestroy(e1);
-  cleanup();
+  cudaEventRecord(ev[1]); TRY_(cudaEventSynchronize(ev[1]));
+  float ms = 0; cudaEventElapsedTime(&ms, ev[0], ev[1]); if (ms_out) *ms_out += ms;
 #undef TRY_
-  S.valid = true; S.grid = g; S.tile = tile;
+  // success: the sorted copy keeps its blocks, everything else goes back to the pool with `pool`
+  pool.keep(S.pos); pool.keep(S.w); pool.keep(S.cell_start); pool.keep(S.item_cell); pool.keep(S.item_off); pool.keep(S.item_cnt);
+  S.valid = true; S.grid = g; S.tile = tile; S.stamp = ++cat->clock;
+  all.push_back(S);
+  *out = &all.back();
   return 0;
 }
 
@@ -534,11 +631,11 @@ extern "C" int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2ma
 namespace fcfc {
 
 static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[3], const double hi[3],
-                        double n1, double n2, int tile, bool half) {
+                        double n1, double n2, int tile, bool half, const Options &opt) {
   Grid best; double best_cost = 1e300;
   const double rxy = std::sqrt(R.r2_xy), rz = R.r_z;
   int kmin = 1, kmax = 12;
-  if (const char *ek = getenv("FCFC_GPU_K")) kmin = kmax = std::max(1, atoi(ek));     // experiment hook: force reach/cell
+  if (opt.k > 0) kmin = kmax = opt.k;     // forced reach / cell
   for (int k = kmin; k <= kmax; k++) {
     Grid g; g.periodic = b->periodic;
     bool ok = true;
@@ -549,7 +646,9 @@ static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[
         int nc = (int) std::floor(L / want);
         if (nc < 1) nc = 1;
         while (nc > 1 && L / nc < want) nc--;
-        g.nc[d] = nc; g.origin[d] = 0; g.cs[d] = L / nc; g.box[d] = L;
+        // the period starts at 0 when the catalogues live in [0, L] (the usual case: one grid for every pair of
+        // catalogues), otherwise at their common minimum
+        g.nc[d] = nc; g.origin[d] = (lo[d] >= 0 && hi[d] <= L) ? 0 : lo[d]; g.cs[d] = L / nc; g.box[d] = L;
       } else {
         const double ext = std::max(hi[d] - lo[d], 1e-30);
         int nc = (int) std::floor(ext / want) + 1;
@@ -614,9 +713,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const long nptab = np ? (b->nptab ? (long) b->nptab : tablen(pbin, np)) : 0;
   if (nstab <= 0 || nstab > (1 << 20) || nptab < 0 || nptab > (1 << 20)) { set_err("invalid lookup table length"); return FCFC_GPU_ERR_ARG; }
 
-  cudaEvent_t ev0, ev1, ev2, ev3;
-  cudaEventCreate(&ev0); cudaEventCreate(&ev1); cudaEventCreate(&ev2); cudaEventCreate(&ev3);
-  cudaEventRecord(ev0);
+  const Options opt = options_snapshot();
   memset(&g_stats, 0, sizeof g_stats);
 
   // ---- grid, cell lists, stencil ----
@@ -643,13 +740,17 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     if (dev_hist) cudaMemset(dev_hist, 0, ntot * 8);
     return 0;
   }
-  const Grid g = choose_grid(b, R, lo, hi, (double) c1->n, (double) c2->n, tile, half);
+  const Grid g = choose_grid(b, R, lo, hi, (double) c1->n, (double) c2->n, tile, half, opt);
   if (g.cs[0] <= 0) { set_err("failed to choose a cell grid"); return FCFC_GPU_ERR_TREE; }
+  EventScope evs(4);            // released on every exit path, like the pool blocks of `pool`
+  PoolScope pool;
+  cudaEventRecord(evs[0]);
   float ms_sort = 0;
-  int e = build_sorted<T>(c1, g, tile, withwt != 0, &ms_sort);
+  Sorted<T> *pS1 = nullptr, *pS2 = nullptr;
+  int e = build_sorted<T>(c1, g, tile, withwt != 0, opt, &ms_sort, &pS1);
   if (e) return e;
-  if (c2 != c1) { e = build_sorted<T>(c2, g, tile, withwt != 0, &ms_sort); if (e) return e; }
-  Sorted<T> &S1 = sorted_of<T>(c1), &S2 = sorted_of<T>(c2);
+  if (c2 != c1) { e = build_sorted<T>(c2, g, tile, withwt != 0, opt, &ms_sort, &pS2); if (e) return e; } else pS2 = pS1;
+  Sorted<T> &S1 = *pS1, &S2 = *pS2;
   std::vector<int4> rows = build_stencil(g, R, half);
   if (rows.size() > (size_t) kMaxRows) { set_err("neighbour stencil too large (%zu rows)", rows.size()); return FCFC_GPU_ERR_TREE; }
 
@@ -676,7 +777,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     for (const int2 &r : rin) dense_rows += r.x <= r.y;
   }
   unsigned char *dbuf = nullptr;
-  CUDA_TRY(pool_alloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool.alloc(&dbuf, o_end), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(cudaMemcpy(dbuf, hbuf.data(), o_end, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
 
   // ---- kernel parameters ----
@@ -684,22 +785,22 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   memset(&P, 0, sizeof P);
   P.pos1 = S1.pos; P.w1 = S1.w; P.pos2 = S2.pos; P.w2 = S2.w; P.cell_start2 = S2.cell_start;
   P.item_cell = S1.item_cell; P.item_off = S1.item_off; P.item_cnt = S1.item_cnt;
-  // shard: contiguous item ranges (cells are visited in memory order; cost balancing by item count)
-  // longest-first order of the work items (cost depends on the secondary catalogue and the stencil)
+  // longest-first order of the work items (cost depends on the secondary catalogue and the stencil); shard `part` of
+  // `nparts` takes the items part, part + nparts, ... of that order (count_kernel.cuh: persistent warp loop)
   int *d_order = nullptr, nsplit = 1;
   {
     // small problems: cut every tile's sweep list so that each warp of the grid still gets several work items
     const long long warps_total = (long long) g_ctx.sm_count * BlockShape<T>::kWarps;
     const int nq_all = (int) rows.size() * (b->periodic ? 3 : 1) + (isauto ? 1 : 0);
-    nsplit = (int) std::min<long long>(std::max<long long>(1, (8 * warps_total * nparts + S1.nitem - 1) / std::max(S1.nitem, 1)), std::max(nq_all, 1));
-    if (const char *es = getenv("FCFC_GPU_NSPLIT")) nsplit = std::max(1, std::min(atoi(es), std::max(nq_all, 1)));
+    const long long ipw = std::max(1, opt.items_per_warp);
+    nsplit = (int) std::min<long long>(std::max<long long>(1, (ipw * warps_total * nparts + S1.nitem - 1) / std::max(S1.nitem, 1)), std::max(nq_all, 1));
+    if (opt.nsplit > 0) nsplit = std::max(1, std::min(opt.nsplit, std::max(nq_all, 1)));
     const int ni = S1.nitem * nsplit;
     float *cost = nullptr, *cost2 = nullptr; int *idx = nullptr; void *tmp = nullptr;
-    auto fail = [&](const char *what) { pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp); pool_free(d_order); pool_free(dbuf); set_err("%s", what); return FCFC_GPU_ERR_TREE; };
-    if (pool_alloc(&cost, (size_t) ni * 4) || pool_alloc(&cost2, (size_t) ni * 4) || pool_alloc(&idx, (size_t) ni * 4) ||
-        pool_alloc(&d_order, (size_t) ni * 4)) return fail("out of device memory for the work-item order");
-    int cost_bits = 1;            // mantissa bits of the cost classes (experiment hook: 23 = exact cost order)
-    if (const char *ecb = getenv("FCFC_GPU_COST_BITS")) cost_bits = std::max(0, std::min(23, atoi(ecb)));
+    auto fail = [&](const char *what) { set_err("%s", what); return FCFC_GPU_ERR_TREE; };
+    if (pool.alloc(&cost, (size_t) ni * 4) || pool.alloc(&cost2, (size_t) ni * 4) || pool.alloc(&idx, (size_t) ni * 4) ||
+        pool.alloc(&d_order, (size_t) ni * 4)) return fail("out of device memory for the work-item order");
+    const int cost_bits = std::max(0, std::min(23, opt.cost_bits));   // mantissa bits of the cost classes (23 = exact cost order)
     const unsigned int keep_mask = 0xffffffffu << (23 - cost_bits);
     if (ni) {
       item_cost_kernel<<<(ni + 255) / 256, 256>>>(S1.item_cell, S1.item_cnt, S1.nitem, nsplit, S2.cell_start, reinterpret_cast<const int4 *>(dbuf + o_rows),
@@ -707,10 +808,10 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
       g_stats.kernel_launches++;
       size_t tb = 0;
       if (cub::DeviceRadixSort::SortPairsDescending(nullptr, tb, cost, cost2, idx, d_order, ni) != cudaSuccess) return fail("cub sort failed");
-      if (pool_alloc(&tmp, tb ? tb : 1)) return fail("out of device memory for the work-item order");
+      if (pool.alloc(&tmp, tb ? tb : 1)) return fail("out of device memory for the work-item order");
       if (cub::DeviceRadixSort::SortPairsDescending(tmp, tb, cost, cost2, idx, d_order, ni) != cudaSuccess) return fail("cub sort failed");
     }
-    pool_free(cost); pool_free(cost2); pool_free(idx); pool_free(tmp);
+    pool.free_now(cost); pool.free_now(cost2); pool.free_now(idx); pool.free_now(tmp);
   }
   P.item_order = d_order; P.nitem = S1.nitem * nsplit; P.nsplit = nsplit; P.part = part; P.nparts = nparts;
   P.work_counter = reinterpret_cast<unsigned int *>(dbuf + o_cnt);
@@ -763,7 +864,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
       P.ptab_is_ident = 1;
       for (long i = 0; i < nptab; i++) { long vv = b->pwidth ? ((const uint16_t *) b->ptab)[i] : ((const uint8_t *) b->ptab)[i]; if (vv != i) P.ptab_is_ident = 0; }
     }
-    if (getenv("FCFC_GPU_NO_TABLE_MATH")) P.mu_is_sqrt = P.stab_is_sqrt = P.ptab_is_ident = 0;
+    if (opt.no_table_math) P.mu_is_sqrt = P.stab_is_sqrt = P.ptab_is_ident = 0;
     // fixed-point scales of the fast bins (count_kernel.cuh, fast_bins): the flag band 2^-k must cover the error
     // budget with a factor >= 2 to spare, and bin * 2^k must stay below 2^23
     int ks = 0, km = 0;
@@ -778,14 +879,14 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const int qwords = (bintype == BIN_ISO) ? (withwt ? 2 : 1) : (b->periodic ? (withwt ? 4 : 2) : 4);
   // weighted sums with few bins: 32 lane-private copies of the shared histogram, so that the FP64 (CAS) atomics
   // of the lanes of a warp never collide on a bin
-  const int hist_copies = (withwt && ntot <= 256 && !getenv("FCFC_GPU_NO_HIST_COPIES")) ? 32 : 1;
+  const int hist_copies = (withwt && ntot <= 256 && !opt.no_hist_copies) ? 32 : 1;
   P.hist_copies = hist_copies;
   auto plan = [&](bool sh, int depth, bool tg) {
     return withwt ? make_smem_plan<T, true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg, hist_copies)
                   : make_smem_plan<T, false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), sh, qwords, depth, tg);
   };
   int qdepth_max = 64;
-  if (const char *envd = getenv("FCFC_GPU_QDEPTH")) qdepth_max = std::max(8, atoi(envd) & ~3);
+  if (opt.qdepth > 0) qdepth_max = std::max(8, opt.qdepth & ~3);
   // preference order: everything in shared memory with deep queues > tables in global memory >
   // shallow queues > histogram in global memory (large tables / histograms are rare)
   SmemPlan pl{}; int depth = 0; bool tabs_global = false; v.smem_hist = true;
@@ -793,9 +894,9 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
                                                      {false, false, 16}, {false, true, 8}};
   // fast variants whose s and mu bins are computed never read the tables in the hot loop: leave them in
   // global memory (the exact re-binning of flagged pairs reads them there) and give the space to the stacks
-  const bool fast_variant = !generic && !getenv("FCFC_GPU_FORCE_GENERIC") && (b->periodic || bintype == BIN_ISO);
+  const bool fast_variant = !generic && !opt.force_generic && (b->periodic || bintype == BIN_ISO);
   const bool tables_unused = fast_variant && P.stab_is_sqrt && ((bintype == BIN_SMU && P.mu_is_sqrt) || bintype == BIN_ISO);
-  const bool force_ghist = getenv("FCFC_GPU_GLOBAL_HIST") != nullptr;       // experiment hook
+  const bool force_ghist = opt.global_hist != 0;
   // the packed pair loop (float, box or isotropic, unweighted: PairLoop::kPacked) takes 2 x 4 entries per step and
   // needs that much room above what a drain leaves behind
   const int dmin_variant = (is_float && (b->periodic || bintype == BIN_ISO) && !withwt) ? 12 : 8;
@@ -809,44 +910,42 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     }
     if (depth) break;
   }
-  if (!depth) { pool_free(dbuf); pool_free(d_order); set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
+  if (!depth) { set_err("shared-memory plan does not fit (%d bytes)", pl.total); return FCFC_GPU_ERR_CF; }
   P.tabs_global = tabs_global;
   if (tabs_global && !tables_unused) v.generic = true;   // otherwise only the generic variant reads tables through global pointers
-  if (getenv("FCFC_GPU_FORCE_GENERIC")) v.generic = true;   // test hook: cross-check the fast path against the generic one
+  if (opt.force_generic) v.generic = true;   // cross-check of the fast paths against the generic one
   // dense cells are binned in place by the packed float pair loop of the variants whose drain computes its bins
   // (count_kernel.cuh: kDense, do_chunk_dense)
   // (periodic boxes only: the survey's isotropic float counts could take it too, but no test exercises it there yet)
   const bool dense = is_float && !withwt && bintype != BIN_SPI && b->periodic && !v.generic && v.smem_hist &&
-                     P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt) && sz_rin && !getenv("FCFC_GPU_NO_DENSE");
+                     P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt) && sz_rin && !opt.no_dense;
   P.rows_in = dense ? reinterpret_cast<const int2 *>(dbuf + o_rin) : nullptr;
   P.qdepth = depth;
   P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
-  if (const char *ek = getenv("FCFC_GPU_QKEEP")) P.qkeep = std::max(0, std::min(atoi(ek), depth / 2));       // experiment hook
+  if (opt.qkeep >= 0) P.qkeep = std::max(0, std::min(opt.qkeep, depth / 2));
   P.qkeep = std::max(0, std::min(P.qkeep, depth - 1 - (dmin_variant == 12 ? 8 : 4)));    // a drained stack must have room for the next step
-  cudaEventRecord(ev1);
+  cudaEventRecord(evs[1]);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
   cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
-  cudaEventRecord(ev2);
-  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); pool_free(dbuf); pool_free(d_order); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  cudaEventRecord(evs[2]);
+  if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   // ---- results ----
   cudaError_t ce = cudaMemcpy(withwt ? (void *) cnt_d : (void *) cnt_i, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToHost);
-  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); pool_free(dbuf); pool_free(d_order); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
+  if (ce != cudaSuccess) { set_err("count kernel failed: %s", cudaGetErrorString(ce)); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
   if (dev_hist) cudaMemcpy(dev_hist, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToDevice);
   unsigned long long ev = 0;
   cudaMemcpy(&ev, dbuf + o_cnt + 8, 8, cudaMemcpyDeviceToHost);
-  cudaEventRecord(ev3); cudaEventSynchronize(ev3);
+  cudaEventRecord(evs[3]); cudaEventSynchronize(evs[3]);
   float ms_count = 0, ms_total = 0;
-  cudaEventElapsedTime(&ms_count, ev1, ev2); cudaEventElapsedTime(&ms_total, ev0, ev3);
+  cudaEventElapsedTime(&ms_count, evs[1], evs[2]); cudaEventElapsedTime(&ms_total, evs[0], evs[3]);
   g_stats.pair_evals = ev;
   if (!withwt && cnt_i) { unsigned long long t = 0; for (size_t i = 0; i < ntot; i++) t += (unsigned long long) cnt_i[i]; g_stats.pairs_in = t; }
   g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];
   g_stats.nitem = my_items;
   g_stats.dense_rows = dense ? dense_rows : 0;
-  cudaEventDestroy(ev0); cudaEventDestroy(ev1); cudaEventDestroy(ev2); cudaEventDestroy(ev3);
-  pool_free(dbuf); pool_free(d_order);
   return 0;
 }
 
@@ -861,8 +960,16 @@ extern "C" const char *fcfc_gpu_last_error(void) { return g_err.c_str(); }
 
 static void nccl_reset();
 
+extern "C" int fcfc_gpu_set_option(const char *name, long value) {
+  const int e = set_option(name, value);
+  if (e) set_err("unknown option '%s'", name ? name : "(null)");
+  return e;
+}
+
 extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
   g_verbose = verbose;
+  static std::once_flag env_once;
+  std::call_once(env_once, options_from_env);      // FCFC_GPU_TUNE: read once per process, never on the counting path
   nccl_reset();          // communicators belong to a device set
   int count = 0;
   cudaError_t e = cudaGetDeviceCount(&count);
@@ -965,7 +1072,8 @@ extern "C" void fcfc_gpu_catalog_destroy(fcfc_gpu_catalog *c) {
   for (DevCat *dc : c->dev) {
     cudaSetDevice(dc->device);
     pool_free(dc->x); pool_free(dc->y); pool_free(dc->z); pool_free(dc->s); pool_free(dc->w);
-    dc->sf.release(); dc->sd.release();
+    for (auto &S : dc->sf) S.release();
+    for (auto &S : dc->sd) S.release();
     delete dc;
   }
   if (g_ctx.ready && !g_ctx.devices.empty()) cudaSetDevice(g_ctx.devices[0]);
@@ -1050,7 +1158,11 @@ extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const 
   std::vector<fcfc_gpu_stats> st(ndev);
   for (int d = 0; d < ndev; d++) {
     cudaSetDevice(c1->dev[d]->device);
-    if (pool_alloc(&dhist[d], ntot * 8) != cudaSuccess) { set_err("out of device memory"); return FCFC_GPU_ERR_MEMORY; }
+    if (pool_alloc(&dhist[d], ntot * 8) != cudaSuccess) {
+      for (int k = 0; k < d; k++) { cudaSetDevice(c1->dev[k]->device); pool_free(dhist[k]); }
+      cudaSetDevice(c1->dev[0]->device);
+      set_err("out of device memory"); return FCFC_GPU_ERR_MEMORY;
+    }
   }
   std::vector<std::thread> th;
   for (int d = 0; d < ndev; d++)

@@ -143,6 +143,13 @@ int fcfc_gpu_count_partial(fcfc_gpu_catalog *cat1, fcfc_gpu_catalog *cat2, const
 
 int fcfc_gpu_get_stats(fcfc_gpu_stats *out);
 
+/* Tuning / diagnostic options of the engine (tests and A/B measurements; the defaults are what production uses).
+ * The counting path never reads the environment: FCFC_GPU_TUNE="name=value,..." is parsed once by fcfc_gpu_init,
+ * and this call changes a value explicitly.  Names: k (cells of reach / k), nsplit, items_per_warp, cost_bits,
+ * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter,
+ * sorted_copies; "defaults" restores everything.  Returns FCFC_GPU_ERR_ARG for an unknown name. */
+int fcfc_gpu_set_option(const char *name, long value);
+
 /* Optional host helper for callers that do not link the FCFC host: builds the rescale factor,
  * rescaled edges and lookup tables exactly as cf_setup does (fcfc/2pt_box/setup_cf.c:385-531,
  * fcfc/2pt/setup_cf.c:432-503, util/create_lut.c:58-140).  `linear` != 0 uses smin/ds (and

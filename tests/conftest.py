@@ -28,5 +28,14 @@ def gpu():
     return F
 
 
+@pytest.fixture
+def tuned(gpu):
+    """Set engine options (fcfc_gpu_set_option) for one test; everything goes back to the defaults afterwards."""
+    def set_(name, value=1):
+        gpu.set_option(name, value)
+    yield set_
+    gpu.set_option("defaults", 0)
+
+
 def have_ref(flavour="dbl_scalar", prog="box"):
     return os.path.exists(os.path.join(ROOT, "oracle", "_ref", flavour, f"ref_driver_{prog}"))

@@ -80,20 +80,20 @@ def test_medium_box_vs_oracle(gpu, prec, kw):
 
 @pytest.mark.parametrize("arith", [0, 1])
 @pytest.mark.parametrize("kw", [dict(bintype=1, smax=42.0, ds=1.0, nmu=50), dict(bintype=0, smax=42.0, ds=1.5)])
-def test_dense_cells_vs_oracle(gpu, kw, arith, monkeypatch):
+def test_dense_cells_vs_oracle(gpu, kw, arith, tuned):
     """The dense-cell path (secondary cells entirely in range are binned in place by the pair loop, count_kernel.cuh:
     do_chunk_dense) needs full tiles: 25k points in a box of 7^3 cells of a third of the maximum separation (forced
-    with FCFC_GPU_K) give ~73 points per cell and seven dense offsets.  Counts must equal the oracle's and those of
+    with the engine option k) give ~73 points per cell and seven dense offsets.  Counts must equal the oracle's and those of
     the same engine with the path switched off; auto and cross counts."""
     a, b = box_catalog(25000, 100.0, 41, weights=False), box_catalog(20000, 100.0, 42, weights=False)
-    monkeypatch.setenv("FCFC_GPU_K", "3")
+    tuned("k", 3)
     bins = gpu.Bins(periodic=True, prec="float", arith=arith, box=100.0, **kw)
     ga, gb = gpu.Catalog(*a, bins=bins), gpu.Catalog(*b, bins=bins)
     on = {}
     for name, c2 in (("DD", None), ("DR", gb)):
         on[name] = gpu.count_pairs(ga, c2, bins)
         assert gpu.stats()["dense_rows"] > 0, "the dense path was not used"
-    monkeypatch.setenv("FCFC_GPU_NO_DENSE", "1")
+    tuned("no_dense", 1)
     for name, c2 in (("DD", None), ("DR", gb)):
         off = gpu.count_pairs(ga, c2, bins)
         assert gpu.stats()["dense_rows"] == 0
@@ -242,11 +242,11 @@ def test_medium_survey_smu_vs_oracle(gpu, prec, arith):
 
 
 @pytest.mark.parametrize("depth,keep", [(8, 0), (8, 4), (12, 1), (16, 8), (24, 3), (64, 0)])
-def test_stack_depth_and_keep(gpu, depth, keep, monkeypatch):
+def test_stack_depth_and_keep(gpu, depth, keep, tuned):
     """The per-lane stacks at every depth the shared-memory plan can choose (shallow ones are what the weighted
     double-precision variants get), with drains that leave nothing / half of the stack: same counts."""
-    monkeypatch.setenv("FCFC_GPU_QDEPTH", str(depth))
-    monkeypatch.setenv("FCFC_GPU_QKEEP", str(keep))
+    tuned("qdepth", depth)
+    tuned("qkeep", keep)
     cat = box_catalog(6000, 250.0, 33)
     for prec in ("float", "double"):
         for kw, withwt in ((dict(bintype=1, smax=40.0, ds=1.0, nmu=30), False), (dict(bintype=0, smax=40.0, ds=2.0), False),
