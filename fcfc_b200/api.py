@@ -239,6 +239,21 @@ class Catalog:
         if not self._h:
             raise FcfcGpuError(last_error())
 
+    @classmethod
+    def from_device(cls, px: int, py: int, pz: int, n: int, *, bins: Bins, pw: int | None = None, px2sum: int | None = None,
+                    prescaled: bool = False) -> "Catalog":
+        """The same from DEVICE pointers to columns of the build's ``real`` type (e.g. slices all-gathered over NVLink
+        by a one-process-per-GPU launcher, fcfc_b200/sharding.py): the C ABI resolves host and device pointers alike."""
+        self = cls.__new__(cls)
+        need_s = (not bins.periodic) and bins.bintype != BIN_ISO
+        sumsq = -1 if (px2sum is not None or not need_s) else bins.arith
+        self.n, self.has_w, self.is_float = n, pw is not None, bins.is_float
+        self._h = lib().fcfc_gpu_catalog_create(px, py, pz, px2sum, pw, n, int(bins.is_float),
+                                                1.0 if prescaled else float(bins.rescale), sumsq)
+        if not self._h:
+            raise FcfcGpuError(last_error())
+        return self
+
     @property
     def wsum(self) -> float:
         return lib().fcfc_gpu_catalog_wsum(self._h)

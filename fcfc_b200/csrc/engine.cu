@@ -991,6 +991,16 @@ extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
     if (verbose) fprintf(stderr, "[fcfc_gpu] device %d: %s, %d SMs\n", d, p.name, p.multiProcessorCount);
   }
   if (g_ctx.devices.empty()) { set_err("no device selected"); return FCFC_GPU_ERR_ARG; }
+  // direct NVLink paths between the devices in use (catalogue replicas are copied device to device); where peer
+  // access is not available the copies are staged by the driver
+  for (int a : g_ctx.devices)
+    for (int b2 : g_ctx.devices) {
+      int can = 0;
+      if (a != b2 && cudaDeviceCanAccessPeer(&can, a, b2) == cudaSuccess && can) {
+        cudaSetDevice(a);
+        if (cudaDeviceEnablePeerAccess(b2, 0) != cudaSuccess) cudaGetLastError();     // (already enabled: fine)
+      }
+    }
   CUDA_TRY(cudaSetDevice(g_ctx.devices[0]), FCFC_GPU_ERR_CUDA);
   g_ctx.ready = true;
   return (int) g_ctx.devices.size();
@@ -1002,6 +1012,8 @@ extern "C" void fcfc_gpu_finalize(void) {
   pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear();
 }
 
+// The catalogue columns arrive as host pointers (the FCFC host's malloc'd reader arrays) or as device pointers (a
+// launcher that all-gathered slices over NVLink): cudaMemcpyDefault resolves either through unified addressing.
 template <class T>
 static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z, const void *s, const void *w,
                           double rescale, int sumsq) {
@@ -1009,21 +1021,22 @@ static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z
   CUDA_TRY(pool_alloc(&c->x, bytes), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(pool_alloc(&c->y, bytes), FCFC_GPU_ERR_MEMORY);
   CUDA_TRY(pool_alloc(&c->z, bytes), FCFC_GPU_ERR_MEMORY);
-  CUDA_TRY(cudaMemcpy(c->x, x, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
-  CUDA_TRY(cudaMemcpy(c->y, y, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
-  CUDA_TRY(cudaMemcpy(c->z, z, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  CUDA_TRY(cudaMemcpy(c->x, x, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
+  CUDA_TRY(cudaMemcpy(c->y, y, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
+  CUDA_TRY(cudaMemcpy(c->z, z, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
   c->has_s = (s != nullptr) || sumsq >= 0;
   if (c->has_s) {
     CUDA_TRY(pool_alloc(&c->s, bytes), FCFC_GPU_ERR_MEMORY);
-    if (s) CUDA_TRY(cudaMemcpy(c->s, s, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+    if (s) CUDA_TRY(cudaMemcpy(c->s, s, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
   }
   c->has_w = w != nullptr;
   if (w) {
     CUDA_TRY(pool_alloc(&c->w, bytes), FCFC_GPU_ERR_MEMORY);
-    CUDA_TRY(cudaMemcpy(c->w, w, n * sizeof(T), cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+    CUDA_TRY(cudaMemcpy(c->w, w, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
   }
+  PoolScope pool;
   unsigned long long *stats = nullptr; double *wsum = nullptr;
-  CUDA_TRY(pool_alloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool.alloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
   wsum = reinterpret_cast<double *>(stats + 8);
   unsigned long long init[9];
   for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
@@ -1037,12 +1050,30 @@ static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z
   }
   unsigned long long out[9];
   CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
-  pool_free(stats);
   if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
   for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
   c->smax = n ? dec_f64(out[6]) : 0;
   double ws; memcpy(&ws, &out[8], 8);
   c->wsum = w ? ws : (double) n;
+  return 0;
+}
+
+// Replica of an uploaded (rescaled, checked) catalogue on another device: device-to-device copies over NVLink /
+// NVSwitch instead of one more pass over the host arrays per GPU -- the replacement of kdtree_broadcast
+// (src/tree/kdtree.c:529-619).  All copies of one replica are asynchronous on that device's default stream, so the
+// replicas of a catalogue fill concurrently.
+static int catalog_replicate(DevCat *dst, const DevCat *src, size_t real_bytes) {
+  const size_t bytes = (src->n ? src->n : 1) * real_bytes, used = src->n * real_bytes;
+  void *const from[5] = {src->x, src->y, src->z, src->s, src->w};
+  void **const to[5] = {&dst->x, &dst->y, &dst->z, &dst->s, &dst->w};
+  for (int k = 0; k < 5; k++) {
+    if (!from[k]) continue;
+    CUDA_TRY(pool_alloc(to[k], bytes), FCFC_GPU_ERR_MEMORY);
+    if (used) CUDA_TRY(cudaMemcpyPeerAsync(*to[k], dst->device, from[k], src->device, used, 0), FCFC_GPU_ERR_CUDA);
+  }
+  dst->has_s = src->has_s; dst->has_w = src->has_w;
+  memcpy(dst->bmin, src->bmin, sizeof dst->bmin); memcpy(dst->bmax, src->bmax, sizeof dst->bmax);
+  dst->smax = src->smax; dst->wsum = src->wsum;
   return 0;
 }
 
@@ -1053,14 +1084,23 @@ extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *
   if (n >= (1ull << 31) - 64) { set_err("catalogue too large for 32-bit point indices"); return nullptr; }
   fcfc_gpu_catalog *c = new fcfc_gpu_catalog();
   c->is_float = is_float; c->n = n; c->has_w = w != nullptr;
-  for (int d : g_ctx.devices) {         // one replica per device (host -> each device)
+  // one replica per device: the first is uploaded from the caller's arrays and prepared (rescale, sums, bounding box,
+  // checks) once; the others are copied from it device to device, concurrently
+  for (size_t i = 0; i < g_ctx.devices.size(); i++) {
+    const int d = g_ctx.devices[i];
     DevCat *dc = new DevCat();
     dc->is_float = is_float; dc->n = n; dc->device = d;
     c->dev.push_back(dc);
     cudaSetDevice(d);
-    int e = is_float ? catalog_upload<float>(dc, x, y, z, x2sum, w, rescale, sumsq_arith)
-                     : catalog_upload<double>(dc, x, y, z, x2sum, w, rescale, sumsq_arith);
+    int e;
+    if (i == 0) e = is_float ? catalog_upload<float>(dc, x, y, z, x2sum, w, rescale, sumsq_arith)
+                             : catalog_upload<double>(dc, x, y, z, x2sum, w, rescale, sumsq_arith);
+    else e = catalog_replicate(dc, c->dev[0], is_float ? sizeof(float) : sizeof(double));
     if (e) { fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
+  }
+  for (size_t i = 1; i < g_ctx.devices.size(); i++) {       // the replicas are complete before anyone counts on them
+    cudaSetDevice(g_ctx.devices[i]);
+    if (cudaStreamSynchronize(0) != cudaSuccess) { set_err("catalogue replication failed: %s", cudaGetErrorString(cudaGetLastError())); fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
   }
   c->wsum = c->dev[0]->wsum;
   cudaSetDevice(g_ctx.devices[0]);

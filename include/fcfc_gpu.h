@@ -113,7 +113,9 @@ void fcfc_gpu_finalize(void);
 const char *fcfc_gpu_last_error(void);
 int fcfc_gpu_abi_version(void);
 
-/* Upload a catalogue (host SoA arrays of `real`) and keep it resident on every device in use.
+/* Upload a catalogue (SoA arrays of `real`; host pointers -- pageable or pinned -- or device pointers, resolved by
+ * unified addressing) and keep it resident on every device in use: the first device reads the caller's arrays,
+ * the others copy from it device to device (replaces kdtree_broadcast, tree/kdtree.c:529-619).
  *   x2sum: survey 4th coordinate x^2+y^2+z^2 as left by data_preprocess (fcfc/2pt/build_tree.c:35);
  *          NULL: computed on the device when the metric needs it, in the order selected by
  *          `sumsq_arith` (FCFC_GPU_ARITH_SCALAR: build_tree.c:59; _FMA: build_tree.c:75-82).

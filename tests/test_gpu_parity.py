@@ -193,6 +193,31 @@ def test_edge_cases(gpu):
 
 
 @pytest.mark.parametrize("prec", ["double", "float"])
+@pytest.mark.parametrize("origin", [-150.0, -300.0, 1234.5, -1e-7])
+def test_box_with_any_origin(gpu, prec, origin):
+    """The reference never range-checks positions: only differences and +-L shifts enter its metric
+    (metric_kdtree.c:55-67, metric_common.c:998), so a box stored as [-L/2, L/2) -- or starting anywhere -- counts
+    like one stored as [0, L).  The cell grid starts at the catalogues' common minimum in that case."""
+    L = 300.0
+    x, y, z = box_catalog(20000, L, 91, weights=False)
+    a = (x + origin, y + origin, z + 0.5 * origin)
+    b = tuple(np.ascontiguousarray(c[:7000][::-1]) for c in a)
+    kw = dict(box=L, bintype=1, smax=30.0, ds=1.5, nmu=25)
+    got = gpu_counts(gpu, kw, True, prec, [a, b], ["DD", "DR"], False)
+    ob = oracle.setup(prec=prec[0], periodic=True, **kw)
+    pa, pb = oracle.preprocess(ob, a), oracle.preprocess(ob, b)
+    np.testing.assert_array_equal(got["DD"], oracle.count(ob, pa))
+    np.testing.assert_array_equal(got["DR"], oracle.count(ob, pa, pb))
+    if prec == "double" and origin == -150.0:
+        # points spread over more than one period are refused loudly
+        F = gpu
+        bins = F.Bins(periodic=True, prec=prec, **kw)
+        bad = F.Catalog(np.append(a[0], origin + 1.5 * L), np.append(a[1], 0.0), np.append(a[2], 0.0), bins=bins)
+        with pytest.raises(F.FcfcGpuError, match="outside one period"):
+            F.count_pairs(bad, None, bins)
+
+
+@pytest.mark.parametrize("prec", ["double", "float"])
 def test_tiny_reach_in_huge_volume(gpu, prec):
     """s_max = 2 in a 20000 box (and a sparse survey volume): one reach per cell would need > 2048 cells per axis,
     the grid falls back to coarser cells.  Pairs are planted so that the histogram is not empty."""
@@ -289,7 +314,7 @@ def test_errors(gpu):
     F = gpu
     b = F.Bins(periodic=True, prec="double", box=100.0, bintype=0, smax=20.0, ds=1.0)
     bad = F.Catalog([1.0, 120.0], [1.0, 2.0], [1.0, 2.0], bins=b)
-    with pytest.raises(F.FcfcGpuError, match="outside the periodic box") as e:
+    with pytest.raises(F.FcfcGpuError, match="outside one period of the box") as e:
         F.count_pairs(bad, None, b)
     assert e.value.code == -21
     bf = F.Bins(periodic=True, prec="float", box=100.0, bintype=0, smax=20.0, ds=1.0)
