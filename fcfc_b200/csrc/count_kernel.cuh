@@ -135,6 +135,10 @@ template <class T> struct CountParams {
   int hist_copies;                      // weighted shared-memory histogram: 32 lane-private copies (few bins) or 1
   int qdepth;                           // entries per lane of the accepted-pair queues (a multiple of 4)
   int qkeep;                            // entries a drain leaves on the fullest stack
+  // float pre-filter of the double-precision kernels (count_kernel_pf.cuh): limits padded by the worst-case float error
+  float pf_d2lim;                       // d^2 (box (s_perp,pi): s_perp^2); survey (s_perp,pi): the searched sphere
+  float pf_plim;                        // box (s_perp,pi): |dz|; survey (s_perp,pi): pi^2 (cylinder test 1)
+  float pf_s2lim;                       // survey (s_perp,pi): s_perp^2 (cylinder test 2)
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
   unsigned long long *gevals;           // [0] candidate pair evaluations

@@ -5,6 +5,7 @@
 // precision x binning x metric x weights x arithmetic order x {fast, generic, global-histogram}.
 #pragma once
 #include "count_kernel.cuh"
+#include "count_kernel_pf.cuh"
 
 namespace fcfc {
 
@@ -38,6 +39,35 @@ static cudaError_t launch_count(const Variant &v, const CountParams<T> &P, int n
     default: return v.box ? launch_l2<T, BIN_SPI, true>(v, P, nb, sm) : launch_l2<T, BIN_SPI, false>(v, P, nb, sm);
   }
 }
+
+// Double precision through the float pre-filter (count_kernel_pf.cuh): shared-memory histogram variants only.
+template <int BIN, bool BOX, bool WT, int ARITH, bool GENERIC>
+cudaError_t launch_variant_pf(const CountParams<double> &P, int nblocks, int smem_bytes);
+
+template <int BIN, bool BOX>
+static cudaError_t launch_pf_l2(const Variant &v, const CountParams<double> &P, int nb, int sm) {
+#define FCFC_PF_PICK(WT, AR) (v.generic ? launch_variant_pf<BIN, BOX, WT, AR, true>(P, nb, sm) : launch_variant_pf<BIN, BOX, WT, AR, false>(P, nb, sm))
+  if (v.wt) return v.arith ? FCFC_PF_PICK(true, 1) : FCFC_PF_PICK(true, 0);
+  return v.arith ? FCFC_PF_PICK(false, 1) : FCFC_PF_PICK(false, 0);
+#undef FCFC_PF_PICK
+}
+static inline cudaError_t launch_count_pf(const Variant &v, const CountParams<double> &P, int nb, int sm) {
+  switch (v.bintype) {
+    case BIN_ISO: return v.box ? launch_pf_l2<BIN_ISO, true>(v, P, nb, sm) : launch_pf_l2<BIN_ISO, false>(v, P, nb, sm);
+    case BIN_SMU: return v.box ? launch_pf_l2<BIN_SMU, true>(v, P, nb, sm) : launch_pf_l2<BIN_SMU, false>(v, P, nb, sm);
+    default: return v.box ? launch_pf_l2<BIN_SPI, true>(v, P, nb, sm) : launch_pf_l2<BIN_SPI, false>(v, P, nb, sm);
+  }
+}
+
+#define FCFC_DEFINE_VARIANT_PF(BIN, BOX, WT, ARITH, GENERIC)                                             \
+  template <> cudaError_t launch_variant_pf<BIN, BOX, WT, ARITH, GENERIC>(                               \
+      const CountParams<double> &P, int nblocks, int smem_bytes) {                                       \
+    auto kern = count_kernel_pf<BIN, BOX, WT, ARITH, GENERIC, true, kR>;                                 \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<nblocks, kPfThreads, smem_bytes>>>(P);                                                        \
+    return cudaGetLastError();                                                                           \
+  }
 
 // Body used by the generated instantiation files.
 #define FCFC_DEFINE_VARIANT(T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST)                                   \

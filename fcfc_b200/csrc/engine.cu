@@ -52,6 +52,58 @@ extern "C" void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int i
   out[2] = up(s2max * (1 + 32 * eps) + 32 * eps * pm);
 }
 
+// Limits of the single-precision pre-filter of the double-precision kernels (count_kernel_pf.cuh), padded so that the
+// filter never drops a pair the exact double-precision tests accept.  Inputs: the limits of the exact tests (s2max:
+// squared separation; box (s_perp,pi): s_perp^2 and pmax; survey (s_perp,pi): s_perp^2 and p2max = pi^2), M = the largest
+// |coordinate| that reaches the filter (periodic shifts included), smax_sq / smin_sq = largest / smallest |x|^2 of the two
+// catalogues (survey).  With u = 2^-24:
+//   a coordinate difference of an accepted pair, formed from float copies:  |dx_f - dx| <= e = 2 u M + 1.01 u r
+//   its squared separation (3 squares, 2 sums, fused or not):               |d2_f - d2| <= E_d = 2 sqrt(k) r e + k e^2 + 6 u r^2
+//   (k = 3, or 2 for s_perp^2 of a box; r = the largest accepted separation), the exact d2 itself carries `slack`;
+//   survey (s_perp,pi), with sd = s1 - s2, st = |x1 + x2|^2 >= st_min = (2 sqrt(smin_sq) - r)^2:
+//     |sd_f - sd| <= E_s = 2.02 u smax_sq,   |st_f - st| <= E_st = 12.1 u smax_sq + E_d
+//     test 1  dd_f < st_f * plim:            plim  = (p2max (1 + 1e-9) + 2 sqrt(p2max / st_min) E_s + E_s^2 / st_min) (1 + 8 u) / (1 - E_st / st_min)
+//     test 2  (d2_f - s2lim) st_f <= dd_f:   s2lim = s2max (1 + 1e-9) + slack + E_d + 4 u p2max + 1.01 p2max E_st / st_min + 2 sqrt(p2max / st_min) E_s
+//   (derivation in DESIGN.md); every e / E is doubled for safety, results are rounded up to float.
+// out[0] = d2 limit (survey (s_perp,pi): the sphere s2max + p2max), out[1] = plim, out[2] = s2lim, out[3] = the relative
+// padding of the tightest limit; returns 1 when the filter is usable (padding below 5 %), 2 when in addition the
+// cylinder tests of the survey (s_perp,pi) filter are, 0 otherwise.
+extern "C" int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max, double pmax, double M, double smax_sq,
+                                         double smin_sq, double out[4]) {
+  const double u = std::ldexp(1.0, -24);
+  auto up = [](double v) { float f = (float) v; if ((double) f < v) f = std::nextafter(f, INFINITY); return (double) f; };
+  const bool cyl_box = periodic && bintype == FCFC_GPU_BIN_SPI, cyl_svy = !periodic && bintype == FCFC_GPU_BIN_SPI;
+  const double r2 = cyl_box ? s2max + pmax * pmax : (cyl_svy ? s2max + pmax : s2max);
+  const double r = std::sqrt(r2);
+  const double slack = (periodic || bintype == FCFC_GPU_BIN_ISO) ? 64 * DBL_EPSILON * M * M : 64 * DBL_EPSILON * (smax_sq + 1);
+  const double e = 2.0 * (2 * u * M + 1.01 * u * r);                    // doubled
+  const int k = cyl_box ? 2 : 3;
+  const double rr = cyl_box ? std::sqrt(s2max) : r;
+  const double Ed = 2 * std::sqrt((double) k) * rr * e + k * e * e + 12 * u * rr * rr;
+  const double lim = (cyl_box ? s2max : r2) * (1 + 1e-9) + slack + Ed;
+  out[0] = up(lim * (1 + 8 * u));
+  out[1] = out[2] = 0;
+  double pad = (out[0] / (cyl_box ? s2max : r2)) - 1;
+  int mode = 1;
+  if (cyl_box) { out[1] = up((pmax + e) * (1 + 8 * u)); pad = std::max(pad, out[1] / pmax - 1); }
+  if (cyl_svy) {
+    const double rmin = std::sqrt(std::max(smin_sq, 0.0));
+    const double stm = (2 * rmin > 1.05 * r) ? (2 * rmin - r) * (2 * rmin - r) : 0;
+    if (stm > 0) {
+      const double Es = 2.0 * 2.02 * u * smax_sq, Est = 2.0 * 12.1 * u * smax_sq + Ed;
+      if (Est < 0.01 * stm) {
+        const double p2 = pmax;   // pi^2
+        const double plim = (p2 * (1 + 1e-9) + 2 * std::sqrt(p2 / stm) * Es + Es * Es / stm) * (1 + 8 * u) / (1 - Est / stm);
+        const double s2lim = s2max * (1 + 1e-9) + slack + Ed + 4 * u * p2 + 1.01 * p2 * Est / stm + 2 * std::sqrt(p2 / stm) * Es;
+        if (plim < 1.05 * p2 && s2lim < 1.05 * s2max + 1e-300) { out[1] = up(plim); out[2] = up(s2lim * (1 + 8 * u)); mode = 2; }
+      }
+    }
+    if (mode != 2) { out[1] = 0; out[2] = 0; }          // cylinder tests off: sphere only
+  }
+  out[3] = pad;
+  return pad < 0.05 ? mode : 0;
+}
+
 namespace fcfc {
 
 // ------------------------------------------------------------------------------------------
@@ -266,7 +318,7 @@ struct DevCat {
   void *x = nullptr, *y = nullptr, *z = nullptr, *s = nullptr, *w = nullptr;   // device SoA of `real`
   bool has_s = false, has_w = false;
   double bmin[3], bmax[3];      // bounding box of the (rescaled) coordinates
-  double smax = 0;              // max of x^2+y^2+z^2
+  double smax = 0, smin = 0;    // max / min of x^2+y^2+z^2
   double wsum = 0;
   // cell-sorted copies, one per (grid, tile) in use: DD, DR and RR of a survey run on different grids (the grid
   // follows the extents and sizes of both catalogues), and each keeps its copy instead of re-sorting on every call
@@ -301,14 +353,14 @@ static inline double dec_f64(unsigned long long u) {
   double d; memcpy(&d, &u, 8); return d;
 }
 
-// stats[0..2] = min xyz, [3..5] = max xyz, [6] = max s (all order-encoded), [7] = #non-finite
+// stats[0..2] = min xyz, [3..5] = max xyz, [6] = max s, [9] = min s (all order-encoded), [7] = #non-finite, [8] = sum of weights
 // Rescales in `real` precision (build_tree.c:121-131) and, when requested, fills the survey's 4th
 // coordinate (2pt/build_tree.c:59 scalar order / :75-82 FMA order).
 template <class T>
 __global__ void prep_kernel(T *x, T *y, T *z, T *s, size_t n, T rescale, int do_rescale, int sumsq,
                             unsigned long long *stats, double *wsum, const T *w) {
   using A = Ar<T>;
-  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, smx = 0, ws = 0;
+  double mn[3] = {1e300, 1e300, 1e300}, mx[3] = {-1e300, -1e300, -1e300}, smx = 0, smn = 1e300, ws = 0;
   unsigned long long bad = 0;
   for (size_t i = blockIdx.x * (size_t) blockDim.x + threadIdx.x; i < n; i += (size_t) gridDim.x * blockDim.x) {
     T a = x[i], b = y[i], c = z[i];
@@ -321,7 +373,7 @@ __global__ void prep_kernel(T *x, T *y, T *z, T *s, size_t n, T rescale, int do_
     if (!(isfinite((double) a) && isfinite((double) b) && isfinite((double) c))) { bad++; continue; }
     mn[0] = fmin(mn[0], (double) a); mn[1] = fmin(mn[1], (double) b); mn[2] = fmin(mn[2], (double) c);
     mx[0] = fmax(mx[0], (double) a); mx[1] = fmax(mx[1], (double) b); mx[2] = fmax(mx[2], (double) c);
-    smx = fmax(smx, (double) ss);
+    smx = fmax(smx, (double) ss); smn = fmin(smn, (double) ss);
     if (w) ws += (double) w[i];
   }
   typedef cub::BlockReduce<double, 256> BR;
@@ -336,6 +388,8 @@ __global__ void prep_kernel(T *x, T *y, T *z, T *s, size_t n, T rescale, int do_
   }
   double v = BR(tmp).Reduce(smx, cub::Max()); __syncthreads();
   if (threadIdx.x == 0) atomicMax(&stats[6], enc_f64(v));
+  v = BR(tmp).Reduce(smn, cub::Min()); __syncthreads();
+  if (threadIdx.x == 0) atomicMin(&stats[9], enc_f64(v));
   v = BR(tmp).Sum(ws); __syncthreads();
   if (threadIdx.x == 0 && w) atomicAdd(wsum, v);
   unsigned long long nb = BRU(tmpu).Sum(bad);
@@ -692,7 +746,7 @@ static Grid choose_grid(const fcfc_gpu_bins *b, const Reach &R, const double lo[
 template <class T>
 static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto, int withwt,
                       int part, int nparts, int64_t *cnt_i, double *cnt_d, void *dev_hist) {
-  const bool is_float = sizeof(T) == 4;
+  constexpr bool is_float = sizeof(T) == 4;
   const int bintype = b->bintype;
   const int ns = b->ns, np = (bintype == BIN_SPI) ? b->np : 0, nmu = (bintype == BIN_SMU) ? b->nmu : 1;
   const size_t ntot = (size_t) ns * (bintype == BIN_ISO ? 1 : (bintype == BIN_SMU ? nmu : np));
@@ -924,10 +978,35 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
   if (opt.qkeep >= 0) P.qkeep = std::max(0, std::min(opt.qkeep, depth / 2));
   P.qkeep = std::max(0, std::min(P.qkeep, depth - 1 - (dmin_variant == 12 ? 8 : 4)));    // a drained stack must have room for the next step
+  // double precision: the float pre-filter (count_kernel_pf.cuh) whenever its padded limits stay tight and its
+  // shared-memory plan fits next to a shared-memory histogram; the plain double kernel otherwise
+  bool use_pf = false;
+  PfPlan ppl{};
+  if (!is_float && !opt.no_prefilter && v.smem_hist) {
+    double lim[4], M = 0;
+    for (int d = 0; d < 3; d++) M = std::max(M, std::max(std::fabs(lo[d]), std::fabs(hi[d])) + (b->periodic ? b->bsize[d] : 0.0));
+    const int mode = fcfc_gpu_prefilter_limits(b->periodic, bintype, s2max, pmax, M, std::max(c1->smax, c2->smax), std::min(c1->smin, c2->smin), lim);
+    if (mode) {
+      for (int tg = tables_unused ? 1 : 0; tg < 2 && !use_pf; tg++) {
+        ppl = withwt ? make_pf_plan<true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, hist_copies, kR)
+                     : make_pf_plan<false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, 1, kR);
+        if (ppl.total + 1024 <= smem_max) {
+          use_pf = true;
+          P.tabs_global = tg;
+          v.generic = generic || opt.force_generic || (tg && !tables_unused);
+        }
+      }
+      if (use_pf) { P.pf_d2lim = (float) lim[0]; P.pf_plim = (float) lim[1]; P.pf_s2lim = (float) lim[2]; }
+    }
+  }
+  g_stats.prefilter = use_pf ? 1 : 0;
   cudaEventRecord(evs[1]);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
-  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + BlockShape<T>::kWarps - 1) / BlockShape<T>::kWarps));
-  cudaError_t le = launch_count<T>(v, P, nblocks, pl.total);
+  const int warps_blk = use_pf ? kPfWarps : BlockShape<T>::kWarps;
+  const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + warps_blk - 1) / warps_blk));
+  cudaError_t le;
+  if constexpr (!is_float) le = use_pf ? launch_count_pf(v, P, nblocks, ppl.total) : launch_count<T>(v, P, nblocks, pl.total);
+  else le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(evs[2]);
   if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
@@ -1036,11 +1115,11 @@ static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z
   }
   PoolScope pool;
   unsigned long long *stats = nullptr; double *wsum = nullptr;
-  CUDA_TRY(pool.alloc(&stats, 8 * 8 + 8), FCFC_GPU_ERR_MEMORY);
+  CUDA_TRY(pool.alloc(&stats, 10 * 8), FCFC_GPU_ERR_MEMORY);
   wsum = reinterpret_cast<double *>(stats + 8);
-  unsigned long long init[9];
+  unsigned long long init[10];
   for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
-  init[6] = 0; init[7] = 0; init[8] = 0;
+  init[6] = 0; init[7] = 0; init[8] = 0; init[9] = ~0ull;
   CUDA_TRY(cudaMemcpy(stats, init, sizeof init, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
   if (n) {
     const int nb = (int) std::min<size_t>((n + 255) / 256, 148 * 8);
@@ -1048,11 +1127,12 @@ static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z
                                 s ? -1 : sumsq, stats, wsum, (const T *) c->w);
     g_stats.kernel_launches++;
   }
-  unsigned long long out[9];
+  unsigned long long out[10];
   CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
   if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
   for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
   c->smax = n ? dec_f64(out[6]) : 0;
+  c->smin = n ? dec_f64(out[9]) : 0;
   double ws; memcpy(&ws, &out[8], 8);
   c->wsum = w ? ws : (double) n;
   return 0;
@@ -1073,7 +1153,7 @@ static int catalog_replicate(DevCat *dst, const DevCat *src, size_t real_bytes) 
   }
   dst->has_s = src->has_s; dst->has_w = src->has_w;
   memcpy(dst->bmin, src->bmin, sizeof dst->bmin); memcpy(dst->bmax, src->bmax, sizeof dst->bmax);
-  dst->smax = src->smax; dst->wsum = src->wsum;
+  dst->smax = src->smax; dst->smin = src->smin; dst->wsum = src->wsum;
   return 0;
 }
 

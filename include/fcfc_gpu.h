@@ -103,6 +103,7 @@ typedef struct {
   int32_t ncell[3];     /* cell grid used                                                         */
   int32_t nitem;        /* number of (cell, tile) work items                                      */
   int32_t dense_rows;   /* stencil rows with cells binned in place (dense-cell path), 0 if unused */
+  int32_t prefilter;    /* 1: double-precision count ran through the float pre-filter kernel               */
 } fcfc_gpu_stats;
 
 /* Bind the calling process to CUDA devices.  ndev <= 0: all visible devices.  `devices` may be
@@ -176,6 +177,10 @@ void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km);
 /* Diagnostics: limits of the division-free pre-tests of the survey (s_perp, pi) metric, rounded up to the build's
  * real type: out[0] searched sphere, out[1] padded p2max, out[2] padded s2max. */
 void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int is_float, double out[3]);
+/* Diagnostics: padded limits of the float pre-filter of the double-precision kernels (see engine.cu for the error
+ * budget); returns 0 (filter not usable), 1 (sphere / box tests) or 2 (survey (s_perp,pi): cylinder tests as well). */
+int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max, double pmax, double maxabs, double smax_sq,
+                              double smin_sq, double out[4]);
 /* Diagnostics: the neighbour-cell stencil (rows (dx, dy, dz_lo, dz_hi)) and the dense sub-range of every row for cells
  * of size cs[3], a spherical reach r2 (squared) and the maximum separation s2max (squared); returns the row count. */
 int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2max, int half, int *rows_out, int *inside_out, int max_rows);
