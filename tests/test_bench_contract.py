@@ -55,3 +55,18 @@ def test_generators():
         assert r.min() >= 1000.0 - 1e-6 and r.max() <= 1700.0 + 1e-6 and 0.75 <= c[3].min() and c[3].max() <= 1.25
     rp = np.sqrt(sum(a ** 2 for a in part[:3]))
     assert rp.max() < 1000.0 * (1 + 0.5 * (1.7 ** 3 - 1)) ** (1 / 3) + 1e-6      # the shrunk sample keeps the inner radius
+
+
+def test_blocked_generators_do_not_depend_on_the_split():
+    """The 10^8-point workloads are generated in 64 seeded blocks so that every rank builds only the rows it uploads:
+    any split into row ranges gives the same catalogue."""
+    wl = dict(bench.WORKLOADS["c4_box_smu_clustered_1e8"], n=64 * 500)
+    full = bench.box_rows(wl, 0, wl["n"])
+    parts = [bench.box_rows(wl, lo, hi) for lo, hi in ((0, 7001), (7001, 20000), (20000, 32000))]
+    assert all(np.array_equal(np.concatenate([p[k] for p in parts]), full[k]) for k in range(3))
+    assert all(0 <= c.min() and c.max() < wl["box"] for c in full)
+    sw = dict(bench.SURVEY_WORKLOADS["c5_svy_spi_wt_2e6_1e8"], nr=64 * 300, nd=1000)
+    f = bench.survey_rows(sw, 1, 0, sw["nr"])
+    q = [bench.survey_rows(sw, 1, a, b) for a, b in ((0, 999), (999, 19200))]
+    assert all(np.array_equal(np.concatenate([p[k] for p in q]), f[k]) for k in range(4))
+    assert len(bench.survey_rows(sw, 0, 100, 300)[0]) == 200
