@@ -166,6 +166,14 @@ const fcfc_gpu_bins *fcfc_gpu_bins_get(const fcfc_gpu_bins_owner *o);
 double fcfc_gpu_bins_rescale(const fcfc_gpu_bins_owner *o);
 void fcfc_gpu_bins_free(fcfc_gpu_bins_owner *o);
 
+/* (ra [deg], dec [deg], redshift) -> comoving Cartesian coordinates, in place (host or device pointers), replacing
+ * cnvt_coord_integr (fcfc/2pt/cnvt_coord.c:321-337) for w = -1 dark energy: Legendre-Gauss quadrature of the given order
+ * with the caller's abscissas / weights (the order >> 1 non-zero ones, then the x = 0 weight of an odd order: the
+ * reference's legauss_x / legauss_w + LEGAUSS_IDX(order), math/legauss.h:49-59).  The comoving distance is bit-identical
+ * to the host's; sin / cos are the CUDA math library's (<= 2 ulp), which is why the shim only uses this on request. */
+int fcfc_gpu_cnvt_coord(void *x, void *y, void *z, size_t n, int is_float, double omega_m, double omega_l,
+    double omega_k, int order, const double *gl_x, const double *gl_w);
+
 /* Measured FP32 instruction issue peak of device 0 (lane-instructions per second of a dependent-
  * free FFMA stream) -- the denominator of the pair-evaluation roofline. */
 double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out);
