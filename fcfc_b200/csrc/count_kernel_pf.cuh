@@ -6,14 +6,15 @@
 //
 //   filter (FP32, packed f32x2, every candidate)   float copies of the staged secondaries and of the tile's primaries,
 //       d^2 from plain differences, compared against limits PADDED by the worst-case float error (the host derives the
-//       padding from the extent of the data, engine.cu: prefilter_limits): a superset of the pairs the exact tests can
-//       accept.  A candidate is recorded as ONE BYTE -- the index j of the staged secondary point -- on a per-lane,
-//       per-primary stack.  A chunk holds 32 secondaries, the stacks are 32 deep and are emptied after every chunk: no
-//       overflow checks, no votes, no early exits in the filter loop;
-//   exact pass (FP64, candidates only)              after each chunk every lane pops its candidates, reads the secondary's
-//       double4 from the staging buffer and evaluates the pair with eval_pair / bin_entry of count_kernel.cuh -- the same
-//       IEEE sequences as the plain double kernel, which restate the reference's (metric_common.c:140-235, 377-534;
-//       2pt/metric_common.c:142-259, 283-460).  The double values decide: results are bit-identical to the plain kernel.
+//       padding from the extent of the data, engine.cu: fcfc_gpu_prefilter_limits): a superset of the pairs the exact
+//       tests can accept.  A candidate is recorded as ONE BIT: every lane keeps, per primary, a 32-bit mask over the 32
+//       secondaries of the staged chunk, in a register.  No stores, no votes, no early exits in the filter loop;
+//   exact pass (FP64, candidates only)              after each chunk, per primary slot r: the warp ORs its masks, walks the
+//       secondaries any lane selected (broadcast read of the secondary's double4 from the staging buffer) and the
+//       selected lanes evaluate the pair with eval_pair / bin_entry of count_kernel.cuh -- the same IEEE sequences as the
+//       plain double kernel, which restate the reference's (metric_common.c:140-235, 377-534; 2pt/metric_common.c:142-259,
+//       283-460).  The double values decide: results are bit-identical to the plain kernel.  The 32 primaries of a slot
+//       are consecutive points of the Morton order inside a cell, so the lanes mostly select the same secondaries.
 //
 // Survey (s_perp, pi) counts accept a thin cylinder inside the searched sphere; their filter adds float versions of the
 // two division-free cylinder tests of eval_pair, again with padded limits.
@@ -29,9 +30,8 @@ namespace fcfc {
 #define FCFC_PF_WARPS 20
 #endif
 constexpr int kPfWarps = FCFC_PF_WARPS, kPfThreads = kPfWarps * 32;
-constexpr int kPfDepth = 32;            // stack entries per (lane, primary): one chunk of secondaries
 
-struct PfPlan { int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_misc, off_warp, per_warp, o_stage_d, o_wbuf, o_stage_f, o_stack, total; };
+struct PfPlan { int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_misc, off_warp, per_warp, o_stage_d, o_wbuf, o_stage_f, total; };
 
 template <bool WT>
 __host__ __device__ inline PfPlan make_pf_plan(int ntot, int nstab_bytes, int nptab_bytes, int nmutab_bytes, int ns, int np, int nrows,
@@ -52,7 +52,7 @@ __host__ __device__ inline PfPlan make_pf_plan(int ntot, int nstab_bytes, int np
   p.o_stage_d = w; w += 32 * 32;                // 32 x double4
   p.o_wbuf = w; w += WT ? 32 * 8 : 0;
   p.o_stage_f = w; w += 512;                    // 16 pairs x (x0 x1 y0 y1) | 16 pairs x (z0 z1 s0 s1)
-  p.o_stack = w; w += rmax * kPfDepth * 32;     // [primary][slot][lane] bytes
+  (void) rmax;
   p.per_warp = w;
   p.total = o + kPfWarps * w;
   return p;
@@ -112,7 +112,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   if (BIN == BIN_SPI) for (int i = threadIdx.x; i <= P.np; i += kPfThreads) s_pbin[i] = P.pbin[i];
   for (int i = threadIdx.x; i < P.nrows; i += kPfThreads) s_rows[i] = P.rows[i];
   if (threadIdx.x == 0) *s_blk_evals = 0;
-  for (int i = threadIdx.x * 16; i < kPfWarps * pl.per_warp; i += kPfThreads * 16)      // stacks and staging start zeroed
+  for (int i = threadIdx.x * 16; i < kPfWarps * pl.per_warp; i += kPfThreads * 16)      // staging starts zeroed
     *reinterpret_cast<uint4 *>(smem + pl.off_warp + i) = make_uint4(0, 0, 0, 0);
   __syncthreads();
 
@@ -121,7 +121,6 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   T *wbuf = reinterpret_cast<T *>(wbase + pl.o_wbuf);
   const unsigned int stage_d_s = (unsigned int) __cvta_generic_to_shared(stage_d);
   const unsigned int stage_f_s = (unsigned int) __cvta_generic_to_shared(wbase + pl.o_stage_f);
-  const unsigned int stack_s = (unsigned int) __cvta_generic_to_shared(wbase + pl.o_stack) + (unsigned int) lane;
   const unsigned int hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
   const unsigned int hstride = 8u * (unsigned int) hcopies, hlane = (hcopies > 1) ? 8u * (unsigned int) lane : 0u;
   const unsigned int dump = hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (unsigned int) lane;
@@ -131,6 +130,9 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   const float f_d2lim = P.pf_d2lim, f_plim = P.pf_plim, f_s2lim = P.pf_s2lim;
   const bool cyl_on = kCyl && f_plim > 0.0f;            // (the host switches the cylinder tests off when their padding would be large)
   unsigned long long my_evals = 0;
+#ifdef FCFC_PF_STATS
+  unsigned long long dbg_steps = 0, dbg_useful = 0;
+#endif
   const int ncy = P.nc[1], ncz = P.nc[2];
 
   while (true) {
@@ -201,17 +203,18 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
           const int nj = min(32, piece_end - c0);
           const bool sf = self && c0 < t0 + cnt;
 
-          // ---- filter: every candidate in FP32, one byte per survivor ----
-          unsigned int top[RMAX];
+          // ---- filter: every candidate in FP32, one bit per survivor ----
+          unsigned int cand[RMAX];              // per primary: the staged secondaries that passed
 #pragma unroll
-          for (int r = 0; r < RMAX; r++) top[r] = stack_s + (unsigned int) (r * kPfDepth * 32);
+          for (int r = 0; r < RMAX; r++) cand[r] = 0u;
           auto filter = [&](auto rtag, auto selftag) {
             constexpr int R = decltype(rtag)::value;
             constexpr bool SELF = decltype(selftag)::value;
-            unsigned int jv = 0;                      // index of the first point of the staged pair
+            unsigned int bit = 1u;                    // mask bit of the first point of the staged pair
+            int jv = 0;
             const unsigned int se = stage_f_s + (unsigned int) ((nj + 1) >> 1) * 16u;
 #pragma unroll 1
-            for (unsigned int sa = stage_f_s; sa != se; sa += 16u, jv += 2u) {
+            for (unsigned int sa = stage_f_s; sa != se; sa += 16u, bit <<= 2, jv += 2) {
               f32x2 X, Y, Z, S;
               FCFC_LDS_ASM("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
               if (kCyl) FCFC_LDS_ASM("ld.shared.v2.b64 {%0, %1}, [%2+256];" : "=l"(Z), "=l"(S) : "r"(sa));
@@ -248,9 +251,8 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
 #pragma unroll
                 for (int h = 0; h < 2; h++) {
                   bool p = ok[h];
-                  if (SELF) p = p && (c0 + (int) jv + h > t0 + r * 32 + lane);        // unordered pairs once: metric_common.c:2017-2018
-                  asm volatile("{.reg .pred q; setp.ne.s32 q, %1, 0; @q st.shared.u8 [%0], %2; @q add.u32 %0, %0, 32;}"
-                               : "+r"(top[r]) : "r"((int) p), "r"(jv + (unsigned int) h));
+                  if (SELF) p = p && (c0 + jv + h > t0 + r * 32 + lane);        // unordered pairs once: metric_common.c:2017-2018
+                  if (p) cand[r] |= bit << h;
                 }
               }
             }
@@ -268,13 +270,11 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
           // ---- exact pass: the candidates of this chunk in FP64 ----
 #pragma unroll 1
           for (int r = 0; r < nr; r++) {
-            unsigned int tr = top[0];
+            unsigned int mine = cand[0];
 #pragma unroll
-            for (int q = 1; q < RMAX; q++) tr = (r == q) ? top[q] : tr;
-            const unsigned int base = stack_s + (unsigned int) (r * kPfDepth * 32);
-            const int mine = (int) ((tr - base) >> 5);
-            const int mx = __reduce_max_sync(0xffffffffu, mine);
-            if (mx == 0) continue;
+            for (int q = 1; q < RMAX; q++) mine = (r == q) ? cand[q] : mine;
+            unsigned int todo = __reduce_or_sync(0xffffffffu, mine);     // secondaries some lane selected for its primary r
+            if (todo == 0u) continue;
             // this lane's primary r (its candidates only exist when the lane holds a point)
             T ax = 0, ay = 0, az = 0, as = 0, aw = 1;
             const int k = r * 32 + lane;
@@ -287,11 +287,14 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
               if (WT) aw = P.w1[t0 + k];
             }
 #pragma unroll 1
-            for (int q = 0; q < mx; q++) {
-              const bool have = q < mine;
-              unsigned int j;
-              FCFC_LDS_ASM("ld.shared.u8 %0, [%1];" : "=r"(j) : "r"(base + (unsigned int) q * 32u));
-              const Vec4<T> bq = lds_vec4<T>(stage_d_s + j * 32u);
+            while (todo) {
+              const unsigned int j = (unsigned int) __ffs((int) todo) - 1u;
+              todo &= todo - 1u;
+              const bool have = (mine >> j) & 1u;
+#ifdef FCFC_PF_STATS
+              dbg_steps++; dbg_useful += have;
+#endif
+              const Vec4<T> bq = lds_vec4<T>(stage_d_s + j * 32u);        // broadcast: one secondary for the whole warp
               T d2, aux;
               bool ok = eval_pair<T, BIN, BOX, ARITH, GENERIC>(P, ax, ay, az, as, bq, s2lim, d2, aux);
               ok = ok && have;
@@ -370,6 +373,9 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
     }
   }
   if (lane == 0 && my_evals) atomicAdd(P.gevals, my_evals);
+#ifdef FCFC_PF_STATS          // diagnostics build: lane-steps of the exact pass and the useful ones among them
+  atomicAdd(P.gevals + 1, dbg_steps); atomicAdd(P.gevals + 2, dbg_useful);
+#endif
 }
 
 }  // namespace fcfc

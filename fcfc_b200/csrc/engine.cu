@@ -143,7 +143,7 @@ struct Options {
   int no_prefilter = 0;     // 1: double-precision kernels without the float pre-filter
   int sorted_copies = 3;    // cell-sorted copies kept per catalogue and precision (one per grid in use)
 };
-static Options g_opt;
+static Options g_opt, g_opt_base;       // current values; the process defaults (built-in, then FCFC_GPU_TUNE)
 static std::mutex g_opt_mutex;
 
 static int set_option(const char *name, long value) {
@@ -155,7 +155,7 @@ static int set_option(const char *name, long value) {
       {"qdepth", &g_opt.qdepth}, {"qkeep", &g_opt.qkeep}, {"force_generic", &g_opt.force_generic},
       {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter},
       {"sorted_copies", &g_opt.sorted_copies}};
-  if (!strcmp(name, "defaults")) { g_opt = Options(); return 0; }
+  if (!strcmp(name, "defaults")) { g_opt = g_opt_base; return 0; }
   for (auto &t : tab) if (!strcmp(name, t.n)) { *t.p = (int) value; return 0; }
   return FCFC_GPU_ERR_ARG;
 }
@@ -175,6 +175,8 @@ static void options_from_env() {
     if (!key.empty() && set_option(key.c_str(), val) != 0) fprintf(stderr, "[fcfc_gpu] FCFC_GPU_TUNE: unknown option '%s' ignored\n", key.c_str());
     pos = end + 1;
   }
+  std::lock_guard<std::mutex> lock(g_opt_mutex);
+  g_opt_base = g_opt;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1016,6 +1018,14 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   if (dev_hist) cudaMemcpy(dev_hist, dbuf + o_hist, ntot * 8, cudaMemcpyDeviceToDevice);
   unsigned long long ev = 0;
   cudaMemcpy(&ev, dbuf + o_cnt + 8, 8, cudaMemcpyDeviceToHost);
+#ifdef FCFC_PF_STATS
+  if (use_pf) {
+    unsigned long long dbg[2] = {0, 0};
+    cudaMemcpy(dbg, dbuf + o_cnt + 16, 16, cudaMemcpyDeviceToHost);
+    fprintf(stderr, "[fcfc_gpu] pre-filter exact pass: %llu lane-steps, %llu useful (%.3f), %.3f per evaluation\n", dbg[0], dbg[1],
+            dbg[0] ? (double) dbg[1] / dbg[0] : 0.0, ev ? (double) dbg[0] / ev : 0.0);
+  }
+#endif
   cudaEventRecord(evs[3]); cudaEventSynchronize(evs[3]);
   float ms_count = 0, ms_total = 0;
   cudaEventElapsedTime(&ms_count, evs[1], evs[2]); cudaEventElapsedTime(&ms_total, evs[0], evs[3]);
