@@ -139,6 +139,10 @@ template <class T> struct CountParams {
   float pf_d2lim;                       // d^2 (box (s_perp,pi): s_perp^2); survey (s_perp,pi): the searched sphere
   float pf_plim;                        // box (s_perp,pi): |dz|; survey (s_perp,pi): pi^2 (cylinder test 1)
   float pf_s2lim;                       // survey (s_perp,pi): s_perp^2 (cylinder test 2)
+  // double precision at float speed (count_kernel_df.cuh): the cell grid (local origins), the padded range limit of the
+  // float d^2 and the squared separation below which (s,mu) pairs always take the exact path
+  T gorg[3], gcs[3];
+  float df_d2lim, df_s1sq;
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
   unsigned long long *gevals;           // [0] candidate pair evaluations

@@ -6,6 +6,7 @@
 #pragma once
 #include "count_kernel.cuh"
 #include "count_kernel_pf.cuh"
+#include "count_kernel_df.cuh"
 
 namespace fcfc {
 
@@ -66,6 +67,29 @@ static inline cudaError_t launch_count_pf(const Variant &v, const CountParams<do
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
     if (e != cudaSuccess) return e;                                                                      \
     kern<<<nblocks, kPfThreads, smem_bytes>>>(P);                                                        \
+    return cudaGetLastError();                                                                           \
+  }
+
+// Double precision at float speed (count_kernel_df.cuh): box (s,mu) / isotropic and survey isotropic, computed bins.
+template <int BIN, bool BOX, bool WT, int ARITH>
+cudaError_t launch_variant_df(const CountParams<double> &P, int nblocks, int smem_bytes);
+
+template <int LAZY = 0>      // (a template, so that the specialisations of the generated files precede its instantiation)
+static cudaError_t launch_count_df(const Variant &v, const CountParams<double> &P, int nb, int sm) {
+#define FCFC_DF_PICK(BIN, BOX) (v.wt ? (v.arith ? launch_variant_df<BIN, BOX, true, 1>(P, nb, sm) : launch_variant_df<BIN, BOX, true, 0>(P, nb, sm)) \
+                                     : (v.arith ? launch_variant_df<BIN, BOX, false, 1>(P, nb, sm) : launch_variant_df<BIN, BOX, false, 0>(P, nb, sm)))
+  if (v.bintype == BIN_SMU) return FCFC_DF_PICK(BIN_SMU, true);
+  return v.box ? FCFC_DF_PICK(BIN_ISO, true) : FCFC_DF_PICK(BIN_ISO, false);
+#undef FCFC_DF_PICK
+}
+
+#define FCFC_DEFINE_VARIANT_DF(BIN, BOX, WT, ARITH)                                                      \
+  template <> cudaError_t launch_variant_df<BIN, BOX, WT, ARITH>(                                        \
+      const CountParams<double> &P, int nblocks, int smem_bytes) {                                       \
+    auto kern = count_kernel_df<BIN, BOX, WT, ARITH, kR>;                                                \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<nblocks, kDfThreads, smem_bytes>>>(P);                                                        \
     return cudaGetLastError();                                                                           \
   }
 

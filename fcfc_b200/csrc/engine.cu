@@ -104,6 +104,55 @@ extern "C" int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max
   return pad < 0.05 ? mode : 0;
 }
 
+// Error budget of the double-precision-at-float-speed kernel (count_kernel_df.cuh).  Coordinates reach the float
+// arithmetic relative to the centre of the tile's cell: a primary is within cs/2 of it per axis, the secondary of a pair of
+// interest within cs/2 + r (r = the largest accepted separation, padded), so with u = 2^-24 a coordinate difference
+// formed in float differs from the exact one by at most e = u (cs/2) + u (cs/2 + r) + u r (two roundings to float and
+// the subtraction), doubled for safety.  From it:
+//   |d_f - d| <= sqrt(3) e            error of the separation vector, hence of s, on top of the arithmetic error of the
+//                                     computed bins (3e-7 relative per s bin, 4.5e-7 per mu bin: fcfc_gpu_fastbin_scales)
+//   |d2_f - d2| <= 2 sqrt(3) r e + 3 e^2 + 8 u r^2        -> padded range limit d2lim; everything the padding admits lies
+//                                     within the band of the last s edge and is flagged
+//   |nmu mu_f - nmu mu| <= nmu (1 + sqrt(3)) e / s        -> grows at small separations: the band 2^-km must cover it for
+//                                     s >= s1, and pairs with s < s1 are flagged wholesale; km is the value that minimises
+//                                     the flagged fraction 2 * 2^-km + (s1 / r)^3 of uniformly distributed pairs.
+// Returns 1 when the kernel is usable (enough fixed-point bits, flagged fraction below 3 %), else 0.
+extern "C" int fcfc_gpu_df_budget(int ns, int nmu, double s2max, double cs_max, int *ks_out, int *km_out, double *d2lim_out,
+                                  double *s1sq_out, double *flagged_out) {
+  const double u = std::ldexp(1.0, -24);
+  const double r = std::sqrt(s2max) * (1 + 1e-3);
+  const double e = 2.0 * (u * 0.5 * cs_max + u * (0.5 * cs_max + r) + u * r);
+  auto fits = [](int k, int nbin) { return (double) (nbin + 2) * std::ldexp(1.0, k) < 8388608.0; };
+  // s: band unit 2^-ks >= 2.5 x (arithmetic + coordinate error)
+  const double err_s = 3e-7 * (ns + 1) + 1.7321 * e + 4 * u * r;
+  int ks = 20;
+  while (ks > 4 && (std::ldexp(1.0, -ks) < 2.5 * err_s || !fits(ks, ns))) ks--;
+  int km = 0;
+  double s1 = 0, best = 1e300;
+  if (nmu > 1) {
+    for (int k = 6; k <= 20; k++) {
+      if (!fits(k, nmu)) break;
+      const double band = std::ldexp(1.0, -k) - 2.2 * 4.5e-7 * (nmu + 1);
+      if (band <= 0) break;
+      const double s1k = 2.2 * nmu * 2.7321 * e / band;
+      const double f = 2 * std::ldexp(1.0, -k) + std::pow(std::min(1.0, s1k / r), 3);
+      if (f < best) { best = f; km = k; s1 = s1k; }
+    }
+  } else { km = 20; best = 0; }
+  const double Ed = 2 * 1.7321 * r * e + 3 * e * e + 8 * u * r * r;
+  float lim = (float) ((s2max + Ed) * (1 + 8 * u));
+  if ((double) lim < (s2max + Ed) * (1 + 8 * u)) lim = std::nextafter(lim, INFINITY);
+  float s1sq = (float) (s1 * s1);
+  if ((double) s1sq < s1 * s1) s1sq = std::nextafter(s1sq, INFINITY);
+  const double flagged = best + 4 * std::ldexp(1.0, -ks);
+  if (ks_out) *ks_out = ks;
+  if (km_out) *km_out = km;
+  if (d2lim_out) *d2lim_out = lim;
+  if (s1sq_out) *s1sq_out = (nmu > 1) ? s1sq : 0.0;
+  if (flagged_out) *flagged_out = flagged;
+  return (ks >= 6 && km >= 6 && flagged < 0.03) ? 1 : 0;
+}
+
 namespace fcfc {
 
 // ------------------------------------------------------------------------------------------
@@ -141,6 +190,8 @@ struct Options {
   int global_hist = 0;      // 1: histogram in global memory
   int no_dense = 0;         // 1: dense-cell path off
   int no_prefilter = 0;     // 1: double-precision kernels without the float pre-filter
+  int force_prefilter = 0;  // 1: take the pre-filter kernel whenever it is usable (A/B runs), not only where it was measured faster
+  int no_df = 0;            // 1: double-precision box / isotropic counts without the float-speed kernel (count_kernel_df.cuh)
   int sorted_copies = 3;    // cell-sorted copies kept per catalogue and precision (one per grid in use)
 };
 static Options g_opt, g_opt_base;       // current values; the process defaults (built-in, then FCFC_GPU_TUNE)
@@ -153,7 +204,7 @@ static int set_option(const char *name, long value) {
       {"k", &g_opt.k}, {"nsplit", &g_opt.nsplit}, {"items_per_warp", &g_opt.items_per_warp}, {"cost_bits", &g_opt.cost_bits},
       {"no_subsort", &g_opt.no_subsort}, {"no_table_math", &g_opt.no_table_math}, {"no_hist_copies", &g_opt.no_hist_copies},
       {"qdepth", &g_opt.qdepth}, {"qkeep", &g_opt.qkeep}, {"force_generic", &g_opt.force_generic},
-      {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter},
+      {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter}, {"force_prefilter", &g_opt.force_prefilter}, {"no_df", &g_opt.no_df},
       {"sorted_copies", &g_opt.sorted_copies}};
   if (!strcmp(name, "defaults")) { g_opt = g_opt_base; return 0; }
   for (auto &t : tab) if (!strcmp(name, t.n)) { *t.p = (int) value; return 0; }
@@ -980,11 +1031,35 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   P.qkeep = (depth >= 32) ? depth / 8 : depth / 4;     // measured on the bench workload (depth 32): 1/8 beats 1/4 and 0; shallow stacks prefer 1/4
   if (opt.qkeep >= 0) P.qkeep = std::max(0, std::min(opt.qkeep, depth / 2));
   P.qkeep = std::max(0, std::min(P.qkeep, depth - 1 - (dmin_variant == 12 ? 8 : 4)));    // a drained stack must have room for the next step
-  // double precision: the float pre-filter (count_kernel_pf.cuh) whenever its padded limits stay tight and its
-  // shared-memory plan fits next to a shared-memory histogram; the plain double kernel otherwise
+  // double precision, box (s,mu) / isotropic and survey isotropic counts with computed bins: all bulk work in FP32 on
+  // cell-relative coordinates, the few pairs within rounding distance of an edge re-evaluated in FP64 (count_kernel_df.cuh)
+  bool use_df = false;
+  DfPlan dpl{};
+  if (!is_float && !opt.no_df && !opt.force_prefilter && !v.generic && v.smem_hist && bintype != BIN_SPI && (b->periodic || bintype == BIN_ISO) &&
+      P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt)) {
+    int ks = 0, km = 0;
+    double d2lim = 0, s1sq = 0, flagged = 0;
+    const double cs_max = std::max(g.cs[0], std::max(g.cs[1], g.cs[2]));
+    if (fcfc_gpu_df_budget(ns, bintype == BIN_SMU ? nmu : 1, s2max, cs_max, &ks, &km, &d2lim, &s1sq, &flagged)) {
+      dpl = withwt ? make_df_plan<true>((int) ntot, ns, (int) rows.size(), hist_copies) : make_df_plan<false>((int) ntot, ns, (int) rows.size(), 1);
+      if (dpl.total + 1024 <= smem_max) {
+        use_df = true;
+        P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
+        P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
+        P.fb_smul = 1u << (32 - ks); P.fb_mmul = 1u << (32 - km);
+        P.fb_bias = (0x4B000000u >> ks) + ((bintype == BIN_SMU) ? (0x4B000000u >> km) * (unsigned int) ns : 0u);
+        P.df_d2lim = (float) d2lim; P.df_s1sq = (float) s1sq;
+        for (int d = 0; d < 3; d++) { P.gorg[d] = (T) g.origin[d]; P.gcs[d] = (T) g.cs[d]; }
+        P.tabs_global = 1;
+      }
+    }
+  }
+  // double precision otherwise: the float pre-filter (count_kernel_pf.cuh) where it was measured faster than the plain
+  // double kernel (weighted counts, survey (s,mu) and (s_perp,pi)), whenever its padded limits stay tight and its
+  // shared-memory plan fits next to a shared-memory histogram; the plain double kernel in every other case
   bool use_pf = false;
   PfPlan ppl{};
-  if (!is_float && !opt.no_prefilter && v.smem_hist) {
+  if (!is_float && !use_df && !opt.no_prefilter && v.smem_hist && (withwt || (!b->periodic && bintype != BIN_ISO) || opt.force_prefilter)) {
     double lim[4], M = 0;
     for (int d = 0; d < 3; d++) M = std::max(M, std::max(std::fabs(lo[d]), std::fabs(hi[d])) + (b->periodic ? b->bsize[d] : 0.0));
     const int mode = fcfc_gpu_prefilter_limits(b->periodic, bintype, s2max, pmax, M, std::max(c1->smax, c2->smax), std::min(c1->smin, c2->smin), lim);
@@ -1001,13 +1076,14 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
       if (use_pf) { P.pf_d2lim = (float) lim[0]; P.pf_plim = (float) lim[1]; P.pf_s2lim = (float) lim[2]; }
     }
   }
-  g_stats.prefilter = use_pf ? 1 : 0;
+  g_stats.prefilter = use_df ? 2 : (use_pf ? 1 : 0);
   cudaEventRecord(evs[1]);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
-  const int warps_blk = use_pf ? kPfWarps : BlockShape<T>::kWarps;
+  const int warps_blk = use_df ? kDfWarps : (use_pf ? kPfWarps : BlockShape<T>::kWarps);
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + warps_blk - 1) / warps_blk));
   cudaError_t le;
-  if constexpr (!is_float) le = use_pf ? launch_count_pf(v, P, nblocks, ppl.total) : launch_count<T>(v, P, nblocks, pl.total);
+  if constexpr (!is_float) le = use_df ? launch_count_df(v, P, nblocks, dpl.total)
+                                   : (use_pf ? launch_count_pf(v, P, nblocks, ppl.total) : launch_count<T>(v, P, nblocks, pl.total));
   else le = launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(evs[2]);

@@ -103,7 +103,8 @@ typedef struct {
   int32_t ncell[3];     /* cell grid used                                                         */
   int32_t nitem;        /* number of (cell, tile) work items                                      */
   int32_t dense_rows;   /* stencil rows with cells binned in place (dense-cell path), 0 if unused */
-  int32_t prefilter;    /* 1: double-precision count ran through the float pre-filter kernel               */
+  int32_t prefilter;    /* double-precision counts: 0 plain FP64 kernel, 1 float pre-filter + FP64 pass on the candidates,
+                           2 float-speed kernel (FP32 on cell-relative coordinates, FP64 for the pairs near an edge)   */
 } fcfc_gpu_stats;
 
 /* Bind the calling process to CUDA devices.  ndev <= 0: all visible devices.  `devices` may be
@@ -149,7 +150,7 @@ int fcfc_gpu_get_stats(fcfc_gpu_stats *out);
 /* Tuning / diagnostic options of the engine (tests and A/B measurements; the defaults are what production uses).
  * The counting path never reads the environment: FCFC_GPU_TUNE="name=value,..." is parsed once by fcfc_gpu_init,
  * and this call changes a value explicitly.  Names: k (cells of reach / k), nsplit, items_per_warp, cost_bits,
- * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter,
+ * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter, force_prefilter, no_df,
  * sorted_copies; "defaults" restores everything.  Returns FCFC_GPU_ERR_ARG for an unknown name. */
 int fcfc_gpu_set_option(const char *name, long value);
 
@@ -189,6 +190,12 @@ void fcfc_gpu_survey_pretest_limits(double s2max, double p2max, int is_float, do
  * budget); returns 0 (filter not usable), 1 (sphere / box tests) or 2 (survey (s_perp,pi): cylinder tests as well). */
 int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max, double pmax, double maxabs, double smax_sq,
                               double smin_sq, double out[4]);
+/* Diagnostics: error budget of the double-precision-at-float-speed kernel (count_kernel_df.cuh) for ns unit-width s bins,
+ * nmu mu bins (1: isotropic), the squared maximum separation and the largest cell size: fixed-point scales 2^ks, 2^km, the
+ * padded float range limit, the squared separation below which (s,mu) pairs always take the exact path, and the expected
+ * fraction of flagged pairs; returns 1 when the kernel is usable. */
+int fcfc_gpu_df_budget(int ns, int nmu, double s2max, double cs_max, int *ks, int *km, double *d2lim, double *s1sq,
+                       double *flagged);
 /* Diagnostics: the neighbour-cell stencil (rows (dx, dy, dz_lo, dz_hi)) and the dense sub-range of every row for cells
  * of size cs[3], a spherical reach r2 (squared) and the maximum separation s2max (squared); returns the row count. */
 int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2max, int half, int *rows_out, int *inside_out, int max_rows);
