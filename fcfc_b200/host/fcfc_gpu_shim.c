@@ -16,8 +16,8 @@
 * The same -DSINGLE_PREC / -DWITH_MU_ONE switches as the rest of the host apply.  -DOMP/-DWITH_SIMD
 * may stay enabled for the readers; -DMPI is not supported (one process drives all GPUs).
 *
-* Environment: FCFC_GPU_ARITH=fma selects the FMA evaluation order of the reference's AVX-512 kernels
-* (default: the scalar order, bit-exact against the reference's scalar code path);
+* Environment: FCFC_GPU_ARITH=fma|scalar selects the evaluation order (default: the one this host build would run in the
+* reference: FMA order of the AVX kernels when compiled with -DWITH_SIMD, scalar order otherwise);
 * FCFC_GPU_DEVICES=0,1,... restricts the devices; FCFC_GPU_VERBOSE=1 prints engine diagnostics.
 *******************************************************************************/
 #ifndef _POSIX_C_SOURCE
@@ -32,6 +32,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #ifdef MPI
   #error the GPU engine replaces MPI: build the host without -DMPI
@@ -48,7 +49,13 @@
   #define SHIM_PERIODIC 0
 #endif
 
-static int shim_ready = 0;
+static int shim_ready = 0, shim_verbose = 0;
+
+static double shim_now(void) {
+  struct timespec t;
+  clock_gettime(CLOCK_MONOTONIC, &t);
+  return (double) t.tv_sec + 1e-9 * (double) t.tv_nsec;
+}
 
 static void shim_init(void) {
   if (shim_ready) return;
@@ -60,7 +67,8 @@ static void shim_init(void) {
     free(copy);
   }
   const char *v = getenv("FCFC_GPU_VERBOSE");
-  int n = fcfc_gpu_init(ndev, ndev ? dev : NULL, v ? atoi(v) : 0);
+  shim_verbose = v ? atoi(v) : 0;
+  int n = fcfc_gpu_init(ndev, ndev ? dev : NULL, shim_verbose);
   if (n <= 0) {
     P_ERR("GPU engine initialisation failed: %s\n", fcfc_gpu_last_error());
     exit(FCFC_ERR_TREE);
@@ -77,7 +85,9 @@ static void *shim_upload(real *x[static FCFC_XDIM], real *w, const size_t ndata,
 #if FCFC_XDIM > 3
   s = x[3];
 #endif
+  const double t0 = shim_now();
   fcfc_gpu_catalog *cat = fcfc_gpu_catalog_create(x[0], x[1], x[2], s, w, ndata, SHIM_IS_FLOAT, 1.0, -1);
+  if (shim_verbose && cat) fprintf(stderr, "[fcfc_gpu] catalogue of %zu objects resident on every device: %.1f ms\n", ndata, 1e3 * (shim_now() - t0));
   if (!cat) {
     P_ERR("failed to build the GPU cell list: %s\n", fcfc_gpu_last_error());
     return NULL;
@@ -130,8 +140,14 @@ int count_pairs(const void *tree1, const void *tree2, CF *cf, COUNT *cnt,
 #ifdef WITH_MU_ONE
   b.with_mu_one = 1;
 #endif
+  /* evaluation order: that of the code path this host build would run in the reference -- the AVX/FMA kernels of a
+   * -DWITH_SIMD build (metric_common.c:377-534), the scalar sequence otherwise (:140-235); FCFC_GPU_ARITH overrides */
   const char *ar = getenv("FCFC_GPU_ARITH");
+#if defined(WITH_SIMD)
+  b.arith = (ar && !strcmp(ar, "scalar")) ? FCFC_GPU_ARITH_SCALAR : FCFC_GPU_ARITH_FMA;
+#else
   b.arith = (ar && !strcmp(ar, "fma")) ? FCFC_GPU_ARITH_FMA : FCFC_GPU_ARITH_SCALAR;
+#endif
   b.s2bin = cf->s2bin;
 #ifdef FCFC_METRIC_PERIODIC
   b.pbin = cf->pbin;
@@ -140,8 +156,16 @@ int count_pairs(const void *tree1, const void *tree2, CF *cf, COUNT *cnt,
   b.pbin = cf->p2bin;
 #endif
   b.stab = cf->stab; b.ptab = cf->ptab; b.mutab = cf->mutab;
+  const double t0 = shim_now();
   int e = fcfc_gpu_count((fcfc_gpu_catalog *) tree1, (fcfc_gpu_catalog *) tree2, &b, isauto, withwt,
       withwt ? NULL : (int64_t *) cnt, withwt ? (double *) cnt : NULL);
+  if (shim_verbose && !e) {
+    fcfc_gpu_stats st;
+    fcfc_gpu_get_stats(&st);
+    fprintf(stderr, "[fcfc_gpu] count step: %.1f ms wall (cell lists %.1f ms, counting kernel %.1f ms on the slowest device, "
+        "%.4g pair evaluations, grid %d x %d x %d)\n", 1e3 * (shim_now() - t0), st.ms_sort, st.ms_count, (double) st.pair_evals,
+        st.ncell[0], st.ncell[1], st.ncell[2]);
+  }
   if (e) {
     P_ERR("GPU pair counting failed (%d): %s\n", e, fcfc_gpu_last_error());
     exit(FCFC_ERR_CF);

@@ -23,9 +23,12 @@ def test_in_process_multi_device_matches_single_device():
     cat = box_catalog(300000, 600.0, 91)
     D, R = survey_catalog(30000, 92), survey_catalog(90000, 93)
     res = {}
-    for tag, devs in (("one", [0]), ("all", None)):
+    # "all": histograms summed on the host while the NCCL communicators are still being set up in the background;
+    # "nccl": the count waits for them and all-reduces on the devices
+    for tag, devs in (("one", [0]), ("all", None), ("nccl", None)):
         n = F.init(devices=devs)
         assert n == (1 if devs else _ndev())
+        F.set_option("nccl_wait", 1 if tag == "nccl" else 0)
         out = []
         b = F.Bins(periodic=True, prec="float", arith=1, box=600.0, bintype=1, smax=60.0, ds=1.5, nmu=60)
         g = F.Catalog(*cat[:3], bins=b)
@@ -38,7 +41,12 @@ def test_in_process_multi_device_matches_single_device():
         out.append(F.count_pairs(gd, gr, b, withwt=True)); out.append(F.count_pairs(gr, None, b, withwt=False))
         gd.destroy(); gr.destroy()
         res[tag] = out
+    F.set_option("defaults", 0)
     F.init(devices=[0])
+    np.testing.assert_array_equal(res["one"][0], res["nccl"][0])
+    np.testing.assert_allclose(res["nccl"][1], res["one"][1], rtol=1e-12, atol=0)
+    np.testing.assert_allclose(res["nccl"][2], res["one"][2], rtol=1e-12, atol=0)
+    np.testing.assert_array_equal(res["one"][3], res["nccl"][3])
     np.testing.assert_array_equal(res["one"][0], res["all"][0])
     np.testing.assert_allclose(res["all"][1], res["one"][1], rtol=1e-12, atol=0)
     np.testing.assert_allclose(res["all"][2], res["one"][2], rtol=1e-12, atol=0)
