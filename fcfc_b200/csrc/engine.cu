@@ -194,7 +194,7 @@ struct Options {
   int force_prefilter = 0;  // 1: take the pre-filter kernel whenever it is usable (A/B runs), not only where it was measured faster
   int no_df = 0;            // 1: double-precision box / isotropic counts without the float-speed kernel (count_kernel_df.cuh)
   int sorted_copies = 3;    // cell-sorted copies kept per catalogue and precision (one per grid in use)
-  int nccl_wait = 0;        // 1: a multi-device count waits for the NCCL communicators instead of summing on the host
+  int nccl = 0;             // 1: one process, several devices: combine the histograms with an NCCL all-reduce instead of on the host
 };
 static Options g_opt, g_opt_base;       // current values; the process defaults (built-in, then FCFC_GPU_TUNE)
 static std::mutex g_opt_mutex;
@@ -207,7 +207,7 @@ static int set_option(const char *name, long value) {
       {"no_subsort", &g_opt.no_subsort}, {"no_table_math", &g_opt.no_table_math}, {"no_hist_copies", &g_opt.no_hist_copies},
       {"qdepth", &g_opt.qdepth}, {"qkeep", &g_opt.qkeep}, {"force_generic", &g_opt.force_generic},
       {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter}, {"force_prefilter", &g_opt.force_prefilter}, {"no_df", &g_opt.no_df},
-      {"sorted_copies", &g_opt.sorted_copies}, {"nccl_wait", &g_opt.nccl_wait}};
+      {"sorted_copies", &g_opt.sorted_copies}, {"nccl", &g_opt.nccl}};
   if (!strcmp(name, "defaults")) { g_opt = g_opt_base; return 0; }
   for (auto &t : tab) if (!strcmp(name, t.n)) { *t.p = (int) value; return 0; }
   return FCFC_GPU_ERR_ARG;
@@ -1126,7 +1126,6 @@ extern "C" int fcfc_gpu_abi_version(void) { return FCFC_GPU_ABI_VERSION; }
 extern "C" const char *fcfc_gpu_last_error(void) { return g_err.c_str(); }
 
 static void nccl_reset();
-static void nccl_start_async();
 
 extern "C" int fcfc_gpu_set_option(const char *name, long value) {
   const int e = set_option(name, value);
@@ -1171,7 +1170,6 @@ extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
     }
   CUDA_TRY(cudaSetDevice(g_ctx.devices[0]), FCFC_GPU_ERR_CUDA);
   g_ctx.ready = true;
-  if (g_ctx.devices.size() > 1) nccl_start_async();
   return (int) g_ctx.devices.size();
 }
 
@@ -1326,14 +1324,13 @@ struct Nccl {
   const char *(*GetErrorString)(int) = nullptr;
   std::vector<void *> comms;
   std::vector<int> devices;           // the device set the communicators were made for
-  std::atomic<bool> ready{false};
-  bool tried = false;
-  std::thread worker;                 // communicator set-up runs beside catalogue reading and upload (it takes about a second)
+  bool ready = false, tried = false;
 };
 Nccl g_nccl;
 bool nccl_setup() {
   if (g_nccl.tried) return g_nccl.ready;
   g_nccl.tried = true;
+  g_nccl.devices = g_ctx.devices;
   for (const char *name : {"libnccl.so.2", "libnccl.so"}) { g_nccl.lib = dlopen(name, RTLD_NOW | RTLD_GLOBAL); if (g_nccl.lib) break; }
   if (!g_nccl.lib) return false;
 #define FCFC_SYM(f, n) g_nccl.f = reinterpret_cast<decltype(g_nccl.f)>(dlsym(g_nccl.lib, n)); if (!g_nccl.f) return false;
@@ -1347,14 +1344,7 @@ bool nccl_setup() {
 }
 }  // namespace
 
-// Started by fcfc_gpu_init when one process drives several devices: ncclCommInitAll in the background.  A count that
-// finishes before the communicators exist adds its ntot-element partial histograms on the host instead of waiting.
-static void nccl_start_async() {
-  g_nccl.devices = g_ctx.devices;
-  g_nccl.worker = std::thread([]() { nccl_setup(); });
-}
 static void nccl_reset() {
-  if (g_nccl.worker.joinable()) g_nccl.worker.join();
   if (g_nccl.ready) for (void *c : g_nccl.comms) if (c) g_nccl.CommDestroy(c);
   g_nccl.comms.clear(); g_nccl.ready = false; g_nccl.tried = false;
 }
@@ -1399,8 +1389,12 @@ extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const 
   int bad = 0;
   for (int d = 0; d < ndev; d++) if (rc[d]) { bad = rc[d]; g_err = errs[d]; }
   if (!bad) {
-    if (options_snapshot().nccl_wait && g_nccl.worker.joinable()) g_nccl.worker.join();
-    if (g_nccl.ready.load()) {
+    // One process driving several devices: the ntot-element partial histograms are already on the host (count_impl reads
+    // them back), and adding them there costs microseconds, whereas ncclCommInitAll costs 1-5 s per process (measured:
+    // a 2-GPU DD count of the 10^7 box took 1.6 s with it, 0.2 s without).  The all-reduce over NVLink is therefore opt-in
+    // here (option nccl = 1); launchers with one process per GPU (bench.py under torchrun) reduce with NCCL as a matter of
+    // course, their communicators exist anyway.
+    if (options_snapshot().nccl && nccl_setup()) {
       int ne = g_nccl.GroupStart();
       for (int d = 0; d < ndev && !ne; d++) {
         cudaSetDevice(c1->dev[d]->device);
@@ -1412,9 +1406,7 @@ extern "C" int fcfc_gpu_count(fcfc_gpu_catalog *c1, fcfc_gpu_catalog *c2, const 
         set_err("NCCL all-reduce of the histograms failed: %s", ne ? g_nccl.GetErrorString(ne) : "copy back"); bad = FCFC_GPU_ERR_CUDA;
       }
     } else {
-      // no NCCL library on this host, or its communicators are still being set up: add the ntot-element partial
-      // histograms that are already on the host (integer sums are exact either way)
-      if (g_verbose) fprintf(stderr, "[fcfc_gpu] NCCL communicators not available (yet): summing the per-device histograms on the host\n");
+      // add the ntot-element partial histograms on the host (integer sums are exact either way)
       for (size_t k = 0; k < ntot; k++) {
         if (withwt) { double v = 0; for (int d = 0; d < ndev; d++) v += reinterpret_cast<double *>(part[d].data())[k]; cnt_d[k] = v; }
         else { int64_t v = 0; for (int d = 0; d < ndev; d++) v += reinterpret_cast<int64_t *>(part[d].data())[k]; cnt_i[k] = v; }

@@ -172,3 +172,76 @@ int count_pairs(const void *tree1, const void *tree2, CF *cf, COUNT *cnt,
   }
   return 0;
 }
+
+
+#ifndef FCFC_METRIC_PERIODIC
+/* Coordinate conversion on the device (opt-in: FCFC_GPU_CNVT=1).  The survey host is linked with
+ * -Wl,--wrap=cnvt_coord (integration/Makefile): cnvt_coord() of the unmodified cnvt_coord.c stays the default -- its
+ * libm sin / cos are what the parity tests are pinned on -- and this wrapper takes over the Legendre-Gauss branch for
+ * w = -1 dark energy on request.  The integration order is chosen exactly as the host does (convergence of the quadrature
+ * at FCFC_INT_NUM_ZSP sample redshifts, cnvt_coord.c:262-305), with the host's own abscissas and weights. */
+#include "cnvt_coord.h"
+#include "legauss.h"
+#include <float.h>
+#include <limits.h>
+#include <math.h>
+
+int __real_cnvt_coord(const CONF *conf, real *x[static 3], const size_t ndata, COORD_CNVT *coord);
+
+static double shim_integrand(const double om, const double ol, const double ok, const double z) {
+  const double z1 = z + 1, z2 = z1 * z1;
+  double d = om * z2 * z1;
+  if (ok) d += ok * z2;
+  d += ol;
+  return SPEED_OF_LIGHT * 0.01 / sqrt(d);
+}
+
+static double shim_legauss(const double om, const double ol, const double ok, const int order, const double z) {
+  const double zp = z * 0.5;
+  double sum = 0;
+  int i = LEGAUSS_IDX(order);
+  for (; i < LEGAUSS_IDX(order) + LEGAUSS_LEN_NONZERO(order); i++) {
+    const double a = zp * (1 + legauss_x[i]), b = zp * (1 - legauss_x[i]);
+    sum += legauss_w[i] * (shim_integrand(om, ol, ok, a) + shim_integrand(om, ol, ok, b));
+  }
+  if (order & 1) sum += legauss_w[i] * shim_integrand(om, ol, ok, zp);
+  return sum * zp;
+}
+
+int __wrap_cnvt_coord(const CONF *conf, real *x[static 3], const size_t ndata, COORD_CNVT *coord) {
+  const char *on = getenv("FCFC_GPU_CNVT");
+  if (!on || !atoi(on) || !conf || conf->fcnvt || conf->dew != -1 || !x || !x[0] || !x[1] || !x[2] || !ndata)
+    return __real_cnvt_coord(conf, x, ndata, coord);
+  shim_init();
+  double zmin = DBL_MAX, zmax = -DBL_MAX;
+  for (size_t i = 0; i < ndata; i++) {
+    const double z = x[2][i];
+    if (z < 0) return __real_cnvt_coord(conf, x, ndata, coord);          /* (the host reports the invalid redshift) */
+    if (z > zmax) zmax = z;
+    if (z < zmin) zmin = z;
+  }
+  int order = 0;
+  for (int k = 0; k < FCFC_INT_NUM_ZSP; k++) {
+    const double z = zmin + k * (zmax - zmin) / (FCFC_INT_NUM_ZSP - 1);
+    double oint, nint = 0;
+    int n = LEGAUSS_MIN_ORDER - 1;
+    do {
+      if (n > LEGAUSS_MAX_ORDER) return __real_cnvt_coord(conf, x, ndata, coord);
+      oint = nint;
+      nint = shim_legauss(conf->omega_m, conf->omega_l, conf->omega_k, ++n, z);
+    } while (fabs(nint - oint) > nint * conf->ecnvt);
+    if (order < n) order = n;
+  }
+  if (order > LEGAUSS_MAX_ORDER) return __real_cnvt_coord(conf, x, ndata, coord);
+  const double t0 = shim_now();
+  const int e = fcfc_gpu_cnvt_coord(x[0], x[1], x[2], ndata, SHIM_IS_FLOAT, conf->omega_m, conf->omega_l, conf->omega_k, order,
+      legauss_x + LEGAUSS_IDX(order), legauss_w + LEGAUSS_IDX(order));
+  if (e) {
+    P_ERR("coordinate conversion on the GPU failed (%d)\n", e);
+    return FCFC_ERR_CNVT;
+  }
+  if (shim_verbose) fprintf(stderr, "[fcfc_gpu] %zu objects converted on the device (Legendre-Gauss order %d): %.1f ms\n", ndata, order, 1e3 * (shim_now() - t0));
+  if (conf->verbose) printf("  Coordinates converted using Legendre-Gauss integration with order %d\n", order);
+  return 0;
+}
+#endif

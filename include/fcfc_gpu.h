@@ -151,7 +151,7 @@ int fcfc_gpu_get_stats(fcfc_gpu_stats *out);
  * The counting path never reads the environment: FCFC_GPU_TUNE="name=value,..." is parsed once by fcfc_gpu_init,
  * and this call changes a value explicitly.  Names: k (cells of reach / k), nsplit, items_per_warp, cost_bits,
  * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter, force_prefilter, no_df,
- * sorted_copies, nccl_wait; "defaults" restores everything.  Returns FCFC_GPU_ERR_ARG for an unknown name. */
+ * sorted_copies, nccl; "defaults" restores everything.  Returns FCFC_GPU_ERR_ARG for an unknown name. */
 int fcfc_gpu_set_option(const char *name, long value);
 
 /* Optional host helper for callers that do not link the FCFC host: builds the rescale factor,

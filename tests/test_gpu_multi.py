@@ -23,12 +23,12 @@ def test_in_process_multi_device_matches_single_device():
     cat = box_catalog(300000, 600.0, 91)
     D, R = survey_catalog(30000, 92), survey_catalog(90000, 93)
     res = {}
-    # "all": histograms summed on the host while the NCCL communicators are still being set up in the background;
-    # "nccl": the count waits for them and all-reduces on the devices
+    # "all": the per-device histograms are added on the host (the default of the in-process path);
+    # "nccl": all-reduced on the devices (option nccl = 1)
     for tag, devs in (("one", [0]), ("all", None), ("nccl", None)):
         n = F.init(devices=devs)
         assert n == (1 if devs else _ndev())
-        F.set_option("nccl_wait", 1 if tag == "nccl" else 0)
+        F.set_option("nccl", 1 if tag == "nccl" else 0)
         out = []
         b = F.Bins(periodic=True, prec="float", arith=1, box=600.0, bintype=1, smax=60.0, ds=1.5, nmu=60)
         g = F.Catalog(*cat[:3], bins=b)
