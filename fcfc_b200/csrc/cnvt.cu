@@ -6,7 +6,7 @@
 // redshifts), then d cos(dec) cos(ra), d cos(dec) sin(ra), d sin(dec).  Every operation of the distance is the
 // reference's, in its order, unfused (the host is compiled as ISO C: no contraction), with IEEE sqrt and division: the
 // comoving DISTANCE is bit-identical to the host's.  sin / cos come from the CUDA math library (<= 2 ulp) instead of the
-// host's libm (<= 1 ulp), so a coordinate can differ from the host's in its last bits: the conversion is therefore
+// host's libm (<= 1 ulp), so a coordinate (two such factors) can differ from the host's by a few ulp -- 5 at most and 15 % of the coordinates in the GPU test: the conversion is therefore
 // opt-in (FCFC_GPU_CNVT=1 in the shim), and the host's own conversion remains the default and the parity path.
 // Only w = -1 dark energy (no pow()) is supported; the shim falls back to the host otherwise.
 #include "../../include/fcfc_gpu.h"

@@ -3,7 +3,7 @@ cnvt_coord_integr (fcfc/2pt/cnvt_coord.c:321-337).
 
 The comoving distance repeats the host's operations one by one (IEEE sqrt / division, no contraction), so it is
 bit-identical; sin / cos come from the CUDA math library (<= 2 ulp) instead of libm (<= 1 ulp), so a Cartesian coordinate
-may differ from the host's in its last bits.  Bars: every coordinate within 4 ulp of the host's, the large majority
+may differ from the host's in its last bits (two such factors per coordinate: up to 5 ulp observed).  Bars: every coordinate within 8 ulp of the host's, the large majority
 identical; and the pair counts of the real command line with FCFC_GPU_CNVT=1 equal to the stock reference's."""
 import ctypes as C
 import filecmp
@@ -55,7 +55,7 @@ def test_device_conversion_matches_host(gpu, order, prec):
     print(f"order {order} {prec}: max {ulp.max():.1f} ulp, identical coordinates {same:.4f}")
     # (coordinates that nearly vanish -- cos close to zero -- are compared on the scale of the distance)
     scale = np.maximum(np.abs(want), 1e-3 * dist[:, None]).astype(dt)
-    assert (np.abs(got.astype(np.float64) - want.astype(np.float64)) <= 4 * np.spacing(scale).astype(np.float64)).all()
+    assert (np.abs(got.astype(np.float64) - want.astype(np.float64)) <= 8 * np.spacing(scale).astype(np.float64)).all()
     assert same > (0.8 if prec == "double" else 0.99)
     # the radial distance: |x| reproduces the host's distance to rounding (the quadrature itself is bit-identical)
     rad = np.sqrt((got.astype(np.float64) ** 2).sum(1))

@@ -24,9 +24,10 @@ except Exception as ex:
 PY
 )"
 }
-timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_parity.py -q -m gpu -x > $O/m${N}_pytest.log 2>&1; el "pytest rc=$?: $(tail -1 $O/m${N}_pytest.log)"
+timeout 600 python -m pytest tests/test_gpu_multi.py tests/test_gpu_cnvt.py tests/test_gpu_parity.py -q -m gpu -x -s > $O/m${N}_pytest.log 2>&1; el "pytest rc=$?: $(tail -1 $O/m${N}_pytest.log)"
 for n in 1 2 4 8; do
   [ $n -le $N ] || continue
+  [ -z "${SKIP_BENCH:-}" ] || continue
   run_bench $n c2_float --steps 5 --warmup 3 --no-cpu --check-shards
   run_bench $n c2_double --steps 5 --warmup 3 --no-cpu --prec double
 done
