@@ -45,7 +45,8 @@ class _CBins(C.Structure):
 class _CStats(C.Structure):
     _fields_ = [("pair_evals", C.c_uint64), ("pairs_in", C.c_uint64), ("ms_sort", C.c_double),
                 ("ms_count", C.c_double), ("ms_total", C.c_double), ("kernel_launches", C.c_uint32),
-                ("ncell", C.c_int32 * 3), ("nitem", C.c_int32), ("dense_rows", C.c_int32), ("prefilter", C.c_int32)]
+                ("ncell", C.c_int32 * 3), ("nitem", C.c_int32), ("dense_rows", C.c_int32), ("prefilter", C.c_int32),
+                ("classified", C.c_int32), ("pair_evals_computed", C.c_uint64)]
 
 
 _lib = None
@@ -297,7 +298,8 @@ def stats() -> dict:
     lib().fcfc_gpu_get_stats(C.byref(s))
     return {"pair_evals": s.pair_evals, "pairs_in": s.pairs_in, "ms_sort": s.ms_sort, "ms_count": s.ms_count,
             "ms_total": s.ms_total, "kernel_launches": s.kernel_launches, "ncell": list(s.ncell), "nitem": s.nitem,
-            "dense_rows": s.dense_rows, "prefilter": s.prefilter}
+            "dense_rows": s.dense_rows, "prefilter": s.prefilter, "classified": s.classified,
+            "pair_evals_computed": s.pair_evals_computed}
 
 
 def measure_fp32_peak() -> tuple[float, float]:

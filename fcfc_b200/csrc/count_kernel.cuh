@@ -143,9 +143,12 @@ template <class T> struct CountParams {
   // float d^2 and the squared separation below which (s,mu) pairs always take the exact path
   T gorg[3], gcs[3];
   float df_d2lim, df_s1sq;
+  // classified staging of the float kernels (count_kernel_cl.cuh): a staged point is dropped when its squared distance to
+  // the nearest point of the tile's box exceeds cl_skip, and binned in place when the farthest corner is within cl_dense
+  float cl_skip, cl_dense;
   // outputs
   unsigned long long *ghist_i; double *ghist_d;
-  unsigned long long *gevals;           // [0] candidate pair evaluations
+  unsigned long long *gevals;           // [0] candidate pair evaluations (n_a * n_b over the swept cell ranges), [3] distance evaluations made (count_kernel_cl.cuh)
 };
 
 // Shared-memory plan (dynamic): [hist][tables][edges][rows][per-warp staging]
@@ -366,12 +369,25 @@ template <int NW> struct QOps<double, NW> {
 #undef FCFC_PUSH_ASM
 
 // Per-lane LIFO of accepted pairs (the order in which pairs reach the histogram is irrelevant).
+// The stacks are columns of a [slot][column] array, and a column is not tied to a lane: the packed pair loop hands every
+// column to the next lane after each step (one SHFL of `top`), so that every column collects the accepted pairs of all
+// lanes in turn.  A lane's acceptance rate follows the position of its primaries in the tile and stays high or low for a
+// whole stencil row; without the rotation the fullest stack fills at the highest rate, the average one at the average rate,
+// and a drain -- every lane pops as many entries as the fullest stack must lose -- runs with idle lanes in that
+// proportion (measured: 55 % of the pop slots useful on the shell of partially accepted points; a simulation of the
+// rotation gives 85-90 %).  Entries are self-contained, so whoever holds a column when the warp drains pops it.
+#ifndef FCFC_ROTATE
+#define FCFC_ROTATE 1
+#endif
 template <class T, int NW> struct LaneQueue {
-  unsigned int top;             // shared address of this lane's next free slot
-  unsigned int base;            // shared address of this lane's slot 0
+  unsigned int top;             // shared address of the next free slot of the column this lane holds
+  unsigned int base;            // shared address of slot 0 of that column (valid outside the rotating pair loop)
+  unsigned int wbase;           // shared address of the warp's queue area (slot 0 of column 0)
   static constexpr unsigned int kStride = 32u * NW * sizeof(T);
   __device__ __forceinline__ void push(const T (&v)[NW], bool ok) { QOps<T, NW>::push(top, v, ok); }
   __device__ __forceinline__ unsigned int fill_bytes() const { return top - base; }
+  __device__ __forceinline__ void rotate(int next_lane) { top = __shfl_sync(0xffffffffu, top, next_lane); }
+  __device__ __forceinline__ void rebase() { base = wbase + ((top - wbase) & (kStride - 1u)); }
 };
 
 // Truncation of 0 <= x < 2^23 (float) / 2^31 (double) without the quarter-rate F2I: add 2^23 (2^52)
@@ -839,13 +855,16 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
     // the loop leaves only when a stack is really about to overflow (a worst-case bound on the pushes would
     // leave every two or three steps at a 50 % acceptance rate).
     constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-    const unsigned int lim = Q.base + (unsigned int) (P.qdepth - 1 - 2 * R) * S;      // proceed while fill + 2 R <= qdepth - 1
+    // proceed while fill + 2 R <= qdepth - 1, i.e. while the slot index of `top` is below qdepth - 2 R (the column offset
+    // is less than one slot row, so one limit serves every column)
+    const unsigned int lim = Q.wbase + (unsigned int) (P.qdepth - 2 * R) * S;
+    const int next_lane = (lane + 1) & 31;
     unsigned int sa = sbuf_s + (unsigned int) (j0 >> 1) * 32u;     // j0 is even: this path always advances by pairs
     const unsigned int sa0 = sa, se = sbuf_s + (unsigned int) ((nj + 1) >> 1) * 32u;
     ub = P.qdepth;                // (no bound is tracked here: whoever needs one next measures the stacks first)
 #pragma unroll kEvalUnroll
     for (; sa != se; sa += 32u) {
-      if (__any_sync(0xffffffffu, Q.top > lim)) break;
+      if (__any_sync(0xffffffffu, Q.top >= lim)) break;
       f32x2 X, Y, Z;
       FCFC_LDS_ASM("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(X), "=l"(Y) : "r"(sa));
       FCFC_LDS_ASM("ld.shared.b64 %0, [%1+16];" : "=l"(Z) : "r"(sa));
@@ -867,7 +886,9 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
           Q.push(e, ok);
         }
       }
+      if (FCFC_ROTATE) Q.rotate(next_lane);
     }
+    if (FCFC_ROTATE) Q.rebase();
     return min(j0 + (int) ((sa - sa0) >> 4), nj);
   }
   // one secondary point per step; as in the packed loop a vote before every step checks the real fill of the stacks
@@ -963,8 +984,8 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   Vec4<T> *sbuf = reinterpret_cast<Vec4<T> *>(smem + pl.off_stage + warp * pl.stage_per_warp);
   T *wbuf = reinterpret_cast<T *>(reinterpret_cast<unsigned char *>(sbuf) + 32 * sizeof(Vec4<T>));
   LaneQueue<T, NW> Q;
-  Q.base = Q.top = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue) + warp * (unsigned int) pl.queue_per_warp
-                   + QOps<T, NW>::lane_offset(lane);
+  Q.wbase = (unsigned int) __cvta_generic_to_shared(smem + pl.off_queue) + warp * (unsigned int) pl.queue_per_warp;
+  Q.base = Q.top = Q.wbase + QOps<T, NW>::lane_offset(lane);
   int ub = 0;                   // warp-uniform upper bound of the fullest lane queue (entries)
   // upper limit of the range test, parked in a vector register (read back from shared memory, which the compiler
   // cannot fold into a constant-bank operand: it would otherwise be re-fetched with LDCU for every secondary point)

@@ -7,6 +7,7 @@
 #include "count_kernel.cuh"
 #include "count_kernel_pf.cuh"
 #include "count_kernel_df.cuh"
+#include "count_kernel_cl.cuh"
 
 namespace fcfc {
 
@@ -90,6 +91,28 @@ static cudaError_t launch_count_df(const Variant &v, const CountParams<double> &
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
     if (e != cudaSuccess) return e;                                                                      \
     kern<<<nblocks, kDfThreads, smem_bytes>>>(P);                                                        \
+    return cudaGetLastError();                                                                           \
+  }
+
+// Single precision with classified staging (count_kernel_cl.cuh): box (s,mu) / isotropic and survey isotropic, computed bins.
+template <int BIN, bool BOX, int ARITH>
+cudaError_t launch_variant_cl(const CountParams<float> &P, int nblocks, int smem_bytes);
+
+template <int LAZY = 0>
+static cudaError_t launch_count_cl(const Variant &v, const CountParams<float> &P, int nb, int sm) {
+#define FCFC_CL_PICK(BIN, BOX) (v.arith ? launch_variant_cl<BIN, BOX, 1>(P, nb, sm) : launch_variant_cl<BIN, BOX, 0>(P, nb, sm))
+  if (v.bintype == BIN_SMU) return FCFC_CL_PICK(BIN_SMU, true);
+  return v.box ? FCFC_CL_PICK(BIN_ISO, true) : FCFC_CL_PICK(BIN_ISO, false);
+#undef FCFC_CL_PICK
+}
+
+#define FCFC_DEFINE_VARIANT_CL(BIN, BOX, ARITH)                                                          \
+  template <> cudaError_t launch_variant_cl<BIN, BOX, ARITH>(                                            \
+      const CountParams<float> &P, int nblocks, int smem_bytes) {                                        \
+    auto kern = count_kernel_cl<BIN, BOX, ARITH, kR>;                                                    \
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
+    if (e != cudaSuccess) return e;                                                                      \
+    kern<<<nblocks, kClThreads, smem_bytes>>>(P);                                                        \
     return cudaGetLastError();                                                                           \
   }
 

@@ -193,6 +193,7 @@ struct Options {
   int no_prefilter = 0;     // 1: double-precision kernels without the float pre-filter
   int force_prefilter = 0;  // 1: take the pre-filter kernel whenever it is usable (A/B runs), not only where it was measured faster
   int no_df = 0;            // 1: double-precision box / isotropic counts without the float-speed kernel (count_kernel_df.cuh)
+  int no_classify = 0;      // 1: single-precision box / isotropic counts without the classified staging (count_kernel_cl.cuh)
   int sorted_copies = 3;    // cell-sorted copies kept per catalogue and precision (one per grid in use)
   int nccl = 0;             // 1: one process, several devices: combine the histograms with an NCCL all-reduce instead of on the host
 };
@@ -206,7 +207,7 @@ static int set_option(const char *name, long value) {
       {"k", &g_opt.k}, {"nsplit", &g_opt.nsplit}, {"items_per_warp", &g_opt.items_per_warp}, {"cost_bits", &g_opt.cost_bits},
       {"no_subsort", &g_opt.no_subsort}, {"no_table_math", &g_opt.no_table_math}, {"no_hist_copies", &g_opt.no_hist_copies},
       {"qdepth", &g_opt.qdepth}, {"qkeep", &g_opt.qkeep}, {"force_generic", &g_opt.force_generic},
-      {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter}, {"force_prefilter", &g_opt.force_prefilter}, {"no_df", &g_opt.no_df},
+      {"global_hist", &g_opt.global_hist}, {"no_dense", &g_opt.no_dense}, {"no_prefilter", &g_opt.no_prefilter}, {"force_prefilter", &g_opt.force_prefilter}, {"no_df", &g_opt.no_df}, {"no_classify", &g_opt.no_classify},
       {"sorted_copies", &g_opt.sorted_copies}, {"nccl", &g_opt.nccl}};
   if (!strcmp(name, "defaults")) { g_opt = g_opt_base; return 0; }
   for (auto &t : tab) if (!strcmp(name, t.n)) { *t.p = (int) value; return 0; }
@@ -1078,15 +1079,43 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
       if (use_pf) { P.pf_d2lim = (float) lim[0]; P.pf_plim = (float) lim[1]; P.pf_s2lim = (float) lim[2]; }
     }
   }
+  // single precision, the same family of counts: classified staging (count_kernel_cl.cuh) -- every staged secondary point is
+  // tested against the tile's bounding box, dropped, binned in place or sent through the ordinary pair loop
+  bool use_cl = false;
+  ClPlan cpl{};
+  if constexpr (is_float) {
+    if (dense && !opt.no_classify) {
+      int cdepth = 0;
+      for (int d = std::min(qdepth_max, 64) & ~3; d >= 12 && !cdepth; d -= 4) {
+        cpl = make_cl_plan((int) ntot, ns, (int) rows.size(), qwords, d);
+        if (cpl.total + 1024 <= smem_max) cdepth = d;
+      }
+      if (cdepth) {
+        use_cl = true;
+        P.qdepth = cdepth;
+        P.qkeep = (cdepth >= 32) ? cdepth / 8 : cdepth / 4;
+        if (opt.qkeep >= 0) P.qkeep = std::max(0, std::min(opt.qkeep, cdepth / 2));
+        P.qkeep = std::max(0, std::min(P.qkeep, cdepth - 1 - 8));
+        // a point is dropped only when its computed distance to the tile's box exceeds the limit by more than every
+        // rounding on the way can account for: the box centre and the shifted coordinates carry a few ulps of the
+        // largest coordinate magnitude (3 ulp(M) per axis: 12 M 2^-23 / r relative in d^2), the evaluations a few ulps
+        // of d^2 itself; the margin is three times that.  The dense limit only steers work (the range test stays).
+        const double margin = 4e-6 * (maxabs / std::sqrt(std::max(s2max, 1e-300))) + 4e-6;
+        P.cl_skip = std::nextafter((float) (s2max * (1.0 + margin)), INFINITY);
+        P.cl_dense = (float) (s2max * (1.0 - margin));
+        P.tabs_global = 1;
+      }
+    }
+  }
   g_stats.prefilter = use_df ? 2 : (use_pf ? 1 : 0);
   cudaEventRecord(evs[1]);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
-  const int warps_blk = use_df ? kDfWarps : (use_pf ? kPfWarps : BlockShape<T>::kWarps);
+  const int warps_blk = use_df ? kDfWarps : (use_pf ? kPfWarps : (use_cl ? kClWarps : BlockShape<T>::kWarps));
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + warps_blk - 1) / warps_blk));
   cudaError_t le;
   if constexpr (!is_float) le = use_df ? launch_count_df(v, P, nblocks, dpl.total)
                                    : (use_pf ? launch_count_pf(v, P, nblocks, ppl.total) : launch_count<T>(v, P, nblocks, pl.total));
-  else le = launch_count<T>(v, P, nblocks, pl.total);
+  else le = use_cl ? launch_count_cl(v, P, nblocks, cpl.total) : launch_count<T>(v, P, nblocks, pl.total);
   g_stats.kernel_launches++;
   cudaEventRecord(evs[2]);
   if (le != cudaSuccess) { set_err("count kernel launch failed: %s", cudaGetErrorString(le)); cudaGetLastError(); return FCFC_GPU_ERR_CF; }
@@ -1108,6 +1137,9 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   float ms_count = 0, ms_total = 0;
   cudaEventElapsedTime(&ms_count, evs[1], evs[2]); cudaEventElapsedTime(&ms_total, evs[0], evs[3]);
   g_stats.pair_evals = ev;
+  g_stats.pair_evals_computed = ev;
+  g_stats.classified = use_cl ? 1 : 0;
+  if (use_cl) { unsigned long long ec = 0; cudaMemcpy(&ec, dbuf + o_cnt + 32, 8, cudaMemcpyDeviceToHost); g_stats.pair_evals_computed = ec; }
   if (!withwt && cnt_i) { unsigned long long t = 0; for (size_t i = 0; i < ntot; i++) t += (unsigned long long) cnt_i[i]; g_stats.pairs_in = t; }
   g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];

@@ -105,6 +105,9 @@ typedef struct {
   int32_t dense_rows;   /* stencil rows with cells binned in place (dense-cell path), 0 if unused */
   int32_t prefilter;    /* double-precision counts: 0 plain FP64 kernel, 1 float pre-filter + FP64 pass on the candidates,
                            2 float-speed kernel (FP32 on cell-relative coordinates, FP64 for the pairs near an edge)   */
+  int32_t classified;   /* 1: staged points were classified against the tile's bounding box (count_kernel_cl.cuh) */
+  uint64_t pair_evals_computed; /* distance evaluations actually made: pair_evals minus the candidates the classification
+                                   dropped wholesale (equal to pair_evals for the other kernels)              */
 } fcfc_gpu_stats;
 
 /* Bind the calling process to CUDA devices.  ndev <= 0: all visible devices.  `devices` may be
@@ -150,7 +153,7 @@ int fcfc_gpu_get_stats(fcfc_gpu_stats *out);
 /* Tuning / diagnostic options of the engine (tests and A/B measurements; the defaults are what production uses).
  * The counting path never reads the environment: FCFC_GPU_TUNE="name=value,..." is parsed once by fcfc_gpu_init,
  * and this call changes a value explicitly.  Names: k (cells of reach / k), nsplit, items_per_warp, cost_bits,
- * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter, force_prefilter, no_df,
+ * no_subsort, no_table_math, no_hist_copies, qdepth, qkeep, force_generic, global_hist, no_dense, no_prefilter,  force_prefilter, no_df, no_classify,
  * sorted_copies, nccl; "defaults" restores everything.  Returns FCFC_GPU_ERR_ARG for an unknown name. */
 int fcfc_gpu_set_option(const char *name, long value);
 

@@ -23,6 +23,6 @@ for bt in (1, 0):
         for _ in range(3):
             c = F.count_pairs(g, None, b); st = F.stats()
             best = min(best, st["ms_count"])
-        print(f"bt={bt} [{s}]: kernel {best:.1f} ms evals {st['pair_evals']:.4g} pairs {int(c.sum())} digest {hashlib.sha1(c.tobytes()).hexdigest()[:12]} grid {st['ncell']}", flush=True)
+        print(f"bt={bt} [{s}]: kernel {best:.1f} ms evals {st['pair_evals']:.4g} computed {st['pair_evals_computed']:.4g} pairs {int(c.sum())} digest {hashlib.sha1(c.tobytes()).hexdigest()[:12]} grid {st['ncell']}", flush=True)
     F.set_option("defaults", 0)
     g.destroy()
