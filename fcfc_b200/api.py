@@ -17,12 +17,13 @@ library is missing or no sm_100 device is usable, calls raise :class:`FcfcGpuErr
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libfcfc_b200.so"
+LIB_PATH = Path(os.environ.get("FCFC_B200_LIB", PKG / "libfcfc_b200.so"))     # (the override serves A/B builds: tools/build_variant.py)
 
 BIN_ISO, BIN_SMU, BIN_SPI = 0, 1, 2
 ARITH_SCALAR, ARITH_FMA = 0, 1

@@ -893,7 +893,8 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
   }
   // one secondary point per step; as in the packed loop a vote before every step checks the real fill of the stacks
   constexpr unsigned int S = LaneQueue<T, NW>::kStride;
-  const unsigned int lim = Q.base + (unsigned int) (P.qdepth - 1 - R) * S;      // proceed while fill + R <= qdepth - 1
+  const unsigned int lim = Q.wbase + (unsigned int) (P.qdepth - R) * S;         // proceed while fill + R <= qdepth - 1 (slot index of `top` below qdepth - R)
+  const int next_lane = (lane + 1) & 31;
   ub = P.qdepth;
   // the staged points are walked with a 32-bit shared-window address (one add per point, no index arithmetic)
   unsigned int sa = (unsigned int) __cvta_generic_to_shared(sbuf + j0);
@@ -901,7 +902,7 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
   int j = j0;
 #pragma unroll kEvalUnroll
   for (; sa != se; sa += (unsigned int) sizeof(Vec4<T>)) {
-    if (__any_sync(0xffffffffu, Q.top > lim)) break;
+    if (__any_sync(0xffffffffu, Q.top >= lim)) break;
     Vec4<T> b;
     if constexpr (kPacked) {      // (only the tile against its own points gets here: SELF) pair layout, one point
       const unsigned int pa = staged_pair_addr(sbuf_s, j);
@@ -923,8 +924,10 @@ __device__ __forceinline__ int do_chunk(const CountParams<T> &P, LaneQueue<T, NW
       else { e[0] = aux; e[1 % NW] = as[r]; e[2 % NW] = b.s; e[3 % NW] = WT ? Ar<T>::mul(aw[r], bw) : (T) 0; }
       Q.push(e, ok);
     }
+    if (FCFC_ROTATE) Q.rotate(next_lane);       // the stack columns move on to the next lane (see LaneQueue)
     j++;
   }
+  if (FCFC_ROTATE) Q.rebase();
   return j;
 }
 
