@@ -105,6 +105,18 @@ extern "C" int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max
   return pad < 0.05 ? mode : 0;
 }
 
+// Limits of the classification of staged points against the tile's bounding box in the single-precision kernels
+// (count_kernel_cl.cuh): a point is dropped when the squared distance to the nearest point of the box, computed in
+// float, exceeds out[0], and binned in place ("dense") when the squared distance to the farthest corner is below
+// out[1].  Only the first must be safe (the dense loop keeps its range test): the box centre and the image-shifted
+// coordinates carry up to 3 ulp(M) per axis (M = largest coordinate magnitude, shifts included), i.e. 12 M 2^-23 / r
+// relative in d^2 at the range limit r, and every evaluation a few ulps of d^2 itself; the margin is three times that.
+extern "C" void fcfc_gpu_classify_limits(double s2max, double maxabs, float out[2]) {
+  const double margin = 4e-6 * (maxabs / std::sqrt(std::max(s2max, 1e-300))) + 4e-6;
+  out[0] = std::nextafter((float) (s2max * (1.0 + margin)), INFINITY);
+  out[1] = (float) (s2max * (1.0 - margin));
+}
+
 // Error budget of the double-precision-at-float-speed kernel (count_kernel_df.cuh).  Coordinates reach the float
 // arithmetic relative to the centre of the tile's cell: a primary is within cs/2 of it per axis, the secondary of a pair of
 // interest within cs/2 + r (r = the largest accepted separation, padded), so with u = 2^-24 a coordinate difference
@@ -1096,13 +1108,10 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
         P.qkeep = (cdepth >= 32) ? cdepth / 8 : cdepth / 4;
         if (opt.qkeep >= 0) P.qkeep = std::max(0, std::min(opt.qkeep, cdepth / 2));
         P.qkeep = std::max(0, std::min(P.qkeep, cdepth - 1 - 8));
-        // a point is dropped only when its computed distance to the tile's box exceeds the limit by more than every
-        // rounding on the way can account for: the box centre and the shifted coordinates carry a few ulps of the
-        // largest coordinate magnitude (3 ulp(M) per axis: 12 M 2^-23 / r relative in d^2), the evaluations a few ulps
-        // of d^2 itself; the margin is three times that.  The dense limit only steers work (the range test stays).
-        const double margin = 4e-6 * (maxabs / std::sqrt(std::max(s2max, 1e-300))) + 4e-6;
-        P.cl_skip = std::nextafter((float) (s2max * (1.0 + margin)), INFINITY);
-        P.cl_dense = (float) (s2max * (1.0 - margin));
+        // (margins: fcfc_gpu_classify_limits)
+        float cl[2];
+        fcfc_gpu_classify_limits(s2max, maxabs, cl);
+        P.cl_skip = cl[0]; P.cl_dense = cl[1];
         P.tabs_global = 1;
       }
     }
@@ -1138,8 +1147,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   cudaEventElapsedTime(&ms_count, evs[1], evs[2]); cudaEventElapsedTime(&ms_total, evs[0], evs[3]);
   g_stats.pair_evals = ev;
   g_stats.pair_evals_computed = ev;
-  g_stats.classified = use_cl ? 1 : 0;
-  if (use_cl) { unsigned long long ec = 0; cudaMemcpy(&ec, dbuf + o_cnt + 32, 8, cudaMemcpyDeviceToHost); g_stats.pair_evals_computed = ec; }
+  g_stats.classified = (use_cl || (use_pf && !b->periodic)) ? 1 : 0;
+  if (use_cl || use_pf) { unsigned long long ec = 0; cudaMemcpy(&ec, dbuf + o_cnt + 32, 8, cudaMemcpyDeviceToHost); g_stats.pair_evals_computed = ec; }
   if (!withwt && cnt_i) { unsigned long long t = 0; for (size_t i = 0; i < ntot; i++) t += (unsigned long long) cnt_i[i]; g_stats.pairs_in = t; }
   g_stats.ms_sort = ms_sort; g_stats.ms_count = ms_count; g_stats.ms_total = ms_total;
   for (int d = 0; d < 3; d++) g_stats.ncell[d] = g.nc[d];

@@ -200,6 +200,11 @@ int fcfc_gpu_prefilter_limits(int periodic, int bintype, double s2max, double pm
  * fraction of flagged pairs; returns 1 when the kernel is usable. */
 int fcfc_gpu_df_budget(int ns, int nmu, double s2max, double cs_max, int *ks, int *km, double *d2lim, double *s1sq,
                        double *flagged);
+/* Diagnostics: limits of the classification of staged points against the tile's bounding box in the single-precision
+ * kernels (count_kernel_cl.cuh) for the squared maximum separation and the largest coordinate magnitude (image shifts
+ * included): out[0] = squared distance to the nearest point of the box above which a point is dropped, out[1] = squared
+ * distance to the farthest corner below which it is binned in place. */
+void fcfc_gpu_classify_limits(double s2max, double maxabs, float out[2]);
 /* Diagnostics: the neighbour-cell stencil (rows (dx, dy, dz_lo, dz_hi)) and the dense sub-range of every row for cells
  * of size cs[3], a spherical reach r2 (squared) and the maximum separation s2max (squared); returns the row count. */
 int fcfc_gpu_debug_stencil(const double cs[3], double r2, double s2max, int half, int *rows_out, int *inside_out, int max_rows);

@@ -33,7 +33,8 @@ def test_library_exports_every_declared_symbol():
 def test_struct_layout_matches_header():
     # 12 int32 + 5 pointers + 2 uint64 + 3 double
     assert ctypes.sizeof(F.api._CBins) == 12 * 4 + 5 * 8 + 2 * 8 + 3 * 8
-    assert ctypes.sizeof(F.api._CStats) == 2 * 8 + 3 * 8 + 4 + 3 * 4 + 4 + 4 + 4 + 4      # (the last 4: tail padding to the 8-byte alignment)
+    # 2 uint64 + 3 double + kernel_launches + ncell[3] + nitem + dense_rows + prefilter + classified (int32 each) + uint64
+    assert ctypes.sizeof(F.api._CStats) == 2 * 8 + 3 * 8 + 4 + 3 * 4 + 4 * 4 + 8
 
 
 @pytest.mark.skipif(os.path.exists("/dev/nvidia0"), reason="a GPU is present")
