@@ -38,6 +38,7 @@ namespace fcfc {
 #define FCFC_CL_WARPS 24
 #endif
 constexpr int kClWarps = FCFC_CL_WARPS, kClThreads = kClWarps * 32;
+constexpr int kClR = 3;                 // primaries per lane: tiles of up to 96 points (the other kernels: 4)
 constexpr int kClRingBytes = 64 * 16;   // 64 points in pair layout: [pair][x0 x1 y0 y1 z0 z1 - -]
 
 struct ClPlan { int off_hist, off_rows, off_misc, off_warp, per_warp, o_ring_d, o_ring_p, o_box, off_queue, queue_per_warp, total; };
@@ -250,15 +251,15 @@ __global__ void __launch_bounds__(kClThreads, 1) count_kernel_cl(const __grid_co
                 switch (nr) {
                   case 1: j = FCFC_CHUNK_DENSE(1); break;
                   case 2: j = FCFC_CHUNK_DENSE(2); break;
-                  case 3: j = FCFC_CHUNK_DENSE(3); break;
-                  default: j = FCFC_CHUNK_DENSE(4); break;
+                  case 3: j = FCFC_CHUNK_DENSE((RMAX < 3 ? RMAX : 3)); break;
+                  default: j = FCFC_CHUNK_DENSE(RMAX); break;
                 }
               } else {
                 switch (nr) {
                   case 1: j = FCFC_CHUNK(1, false); break;
                   case 2: j = FCFC_CHUNK(2, false); break;
-                  case 3: j = FCFC_CHUNK(3, false); break;
-                  default: j = FCFC_CHUNK(4, false); break;
+                  case 3: j = FCFC_CHUNK((RMAX < 3 ? RMAX : 3), false); break;
+                  default: j = FCFC_CHUNK(RMAX, false); break;
                 }
               }
               if (j >= nj) break;

@@ -16,7 +16,7 @@ struct Variant {
   int bintype, arith;
 };
 
-constexpr int kR = 4;   // primary points per lane
+constexpr int kR = 4;   // primary points per lane (a tile holds up to 32 kR points of a cell; count_kernel_cl: kClR)
 
 // Defined (explicitly instantiated) in the generated inst_*.cu files.
 template <class T, int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST>
@@ -109,7 +109,7 @@ static cudaError_t launch_count_cl(const Variant &v, const CountParams<float> &P
 #define FCFC_DEFINE_VARIANT_CL(BIN, BOX, ARITH)                                                          \
   template <> cudaError_t launch_variant_cl<BIN, BOX, ARITH>(                                            \
       const CountParams<float> &P, int nblocks, int smem_bytes) {                                        \
-    auto kern = count_kernel_cl<BIN, BOX, ARITH, kR>;                                                    \
+    auto kern = count_kernel_cl<BIN, BOX, ARITH, kClR>;                                                    \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
     if (e != cudaSuccess) return e;                                                                      \
     kern<<<nblocks, kClThreads, smem_bytes>>>(P);                                                        \
