@@ -105,6 +105,64 @@ def test_dense_cells_vs_oracle(gpu, kw, arith, tuned):
     np.testing.assert_array_equal(on["DR"], oracle.count(ob, pa, pb))
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+@pytest.mark.parametrize("kw", [dict(bintype=1, smax=30.0, ds=1.0, nmu=40), dict(bintype=0, smax=33.0, ds=1.5)])
+@pytest.mark.parametrize("origin", [0.0, -37.5])
+def test_classified_staging_vs_plain(gpu, kw, arith, origin, tuned):
+    """Single-precision box counts take count_kernel_cl (staged points classified against the tile's bounding box, two
+    compacted rings, tiles of 96 points): the statistics must say so -- points were dropped without a distance evaluation --
+    and the counts must equal those of the plain kernel (option no_classify) and of the oracle.  36k points in a 120 box
+    (reach a quarter of it): every periodic image, several tiles per cell in the clustered part, auto and cross."""
+    a = box_catalog(24000, 120.0, 61, weights=False)
+    c = clustered_box_catalog(12000, 120.0, 62)[:3]
+    a = tuple(np.concatenate([u, v]) + origin for u, v in zip(a, c))
+    b = tuple(u + origin for u in box_catalog(9000, 120.0, 63, weights=False))
+    bins = gpu.Bins(periodic=True, prec="float", arith=arith, box=120.0, **kw)
+    ga, gb = gpu.Catalog(*a, bins=bins), gpu.Catalog(*b, bins=bins)
+    on = {}
+    for name, c2 in (("DD", None), ("DR", gb)):
+        on[name] = gpu.count_pairs(ga, c2, bins)
+        st = gpu.stats()
+        assert st["classified"] == 1 and st["pair_evals_computed"] < st["pair_evals"], "classified staging was not used"
+    tuned("no_classify", 1)
+    for name, c2 in (("DD", None), ("DR", gb)):
+        off = gpu.count_pairs(ga, c2, bins)
+        st = gpu.stats()
+        assert st["classified"] == 0 and st["pair_evals_computed"] == st["pair_evals"]
+        np.testing.assert_array_equal(on[name], off)
+    ga.destroy(); gb.destroy()
+    if origin == 0.0:
+        ob = oracle.setup(prec="f", periodic=True, arith=arith, box=120.0, **kw)
+        pa, pb = oracle.preprocess(ob, a), oracle.preprocess(ob, b)
+        np.testing.assert_array_equal(on["DD"], oracle.count(ob, pa))
+        np.testing.assert_array_equal(on["DR"], oracle.count(ob, pa, pb))
+
+
+@pytest.mark.parametrize("kw,withwt", [(dict(bintype=2, smax=24.0, ds=2.0, pmin=0.0, pmax=60.0, dpi=2.0), True),
+                                       (dict(bintype=2, smax=40.0, ds=2.0, pmin=0.0, pmax=30.0, dpi=1.0), False),
+                                       (dict(bintype=1, smax=60.0, ds=3.0, nmu=30), True)])
+def test_survey_classification_vs_plain_double(gpu, kw, withwt, tuned):
+    """Double-precision survey counts take the pre-filter kernel with the per-point classification (sphere and, for
+    (s_perp, pi), the two cylinder bounds) and the dealt exact pass: results must equal the plain FP64 kernel's
+    (option no_prefilter) -- unweighted bit for bit, weighted to 1e-12 with the same empty bins."""
+    D, R = survey_catalog(30000, 71), survey_catalog(90000, 72)
+    cats = [D, R] if withwt else [D[:3], R[:3]]
+    bins = gpu.Bins(periodic=False, prec="double", **kw)
+    g = [gpu.Catalog(*c, bins=bins) for c in cats]
+    got = {}
+    for name, i, j in (("DD", 0, 0), ("DR", 0, 1), ("RR", 1, 1)):
+        got[name] = gpu.count_pairs(g[i], None if i == j else g[j], bins, withwt=withwt)
+        st = gpu.stats()
+        assert st["prefilter"] == 1 and st["classified"] == 1 and st["pair_evals_computed"] < st["pair_evals"]
+    tuned("no_prefilter", 1)
+    for name, i, j in (("DD", 0, 0), ("DR", 0, 1), ("RR", 1, 1)):
+        plain = gpu.count_pairs(g[i], None if i == j else g[j], bins, withwt=withwt)
+        assert gpu.stats()["prefilter"] == 0
+        assert_counts(got[name], plain, withwt)
+    for c in g:
+        c.destroy()
+
+
 @pytest.mark.parametrize("prec", ["double", "float"])
 def test_clustered_cuboid_vs_oracle(gpu, prec):
     cat = clustered_box_catalog(20000, 400.0, 32)
