@@ -251,12 +251,12 @@ __global__ void __launch_bounds__(kDfThreads, 1) count_kernel_df(const __grid_co
           };
           for (int j = 0;;) {
             if (sf) j = chunk(std::integral_constant<int, RMAX>(), std::true_type(), j);
-            else if (RMAX == 4) {
+            else if (RMAX >= 3) {
               switch (nr) {
                 case 1: j = chunk(std::integral_constant<int, 1>(), std::false_type(), j); break;
                 case 2: j = chunk(std::integral_constant<int, 2>(), std::false_type(), j); break;
                 case 3: j = chunk(std::integral_constant<int, 3>(), std::false_type(), j); break;
-                default: j = chunk(std::integral_constant<int, 4>(), std::false_type(), j); break;
+                default: j = chunk(std::integral_constant<int, RMAX>(), std::false_type(), j); break;
               }
             } else j = chunk(std::integral_constant<int, RMAX>(), std::false_type(), j);
             if (j >= nj) break;

@@ -872,7 +872,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const bool cl_candidate = is_float && !withwt && bintype != BIN_SPI && b->periodic && s2bin[0] == 0 && b->swidth == 0 &&
                             b->tabtype == FCFC_GPU_TAB_INT && stab_is_sqrt && (bintype == BIN_ISO || mu_is_sqrt) &&
                             !opt.no_table_math && !opt.no_dense && !opt.no_classify && !opt.force_generic && !opt.global_hist;
-  const int tile = 32 * (cl_candidate ? kClR : kR);
+  const int tile = 32 * (cl_candidate ? kClR : kR);    // (tiles of 96 points were measured for count_kernel_df too: 468.5 -> 474.6 ms)
   const bool half = isauto != 0;
   if (c1->n == 0 || c2->n == 0) {
     if (withwt) { if (cnt_d) memset(cnt_d, 0, ntot * 8); } else if (cnt_i) memset(cnt_i, 0, ntot * 8);
