@@ -132,7 +132,7 @@ template <class T> struct CountParams {
   const T *s2bin; const T *pbin;
   int isauto;
   int tabs_global;                      // lookup tables too large for shared memory: read them from global memory
-  int hist_copies;                      // weighted shared-memory histogram: 32 lane-private copies (few bins) or 1
+  int hist_copies;                      // weighted shared-memory histogram: copies (a power of two <= 32), lane l adds to copy l mod copies
   int qdepth;                           // entries per lane of the accepted-pair queues (a multiple of 4)
   int qkeep;                            // entries a drain leaves on the fullest stack
   // float pre-filter of the double-precision kernels (count_kernel_pf.cuh): limits padded by the worst-case float error
@@ -693,12 +693,14 @@ __device__ __forceinline__ int drain_queue(const CountParams<T> &P, const BlockC
   if (mx + need <= P.qdepth - 1) return mx;
   const int rounds = min((mx - keep + 3) & ~3, 32);     // a multiple of 4 (the fast drain pops four entries per iteration)
   if (rounds <= 0) return 0;
+  __syncwarp();                 // the columns rotate between the lanes: pushes of other lanes must be visible to whoever pops
   if (!GENERIC && SMEMHIST && (BOX || BIN == BIN_ISO)) {
     if (BIN != BIN_SPI && P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt)) drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
     else drain_lut<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);
   } else if (!GENERIC && SMEMHIST && BIN == BIN_SMU && P.stab_is_sqrt && P.mu_is_sqrt) {
     drain_fast<T, BIN, BOX, WT, ARITH, NW>(P, C, F, Q, rounds);       // survey (s,mu): computed bins too (fast_inputs)
   } else drain_generic<T, BIN, BOX, WT, ARITH, GENERIC, SMEMHIST, NW>(P, C, Q, rounds);
+  __syncwarp();                 // ... and the pops complete before another lane pushes into the column
   return max(mx - rounds, 0);
 }
 
@@ -946,7 +948,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   C.hist_u = SMEMHIST ? reinterpret_cast<unsigned int *>(smem + pl.off_hist) : reinterpret_cast<unsigned int *>(P.ghist_i);
   C.hist_d = SMEMHIST ? reinterpret_cast<double *>(smem + pl.off_hist) : P.ghist_d;
   const int hcopies = (WT && SMEMHIST) ? P.hist_copies : 1;
-  C.hmul = hcopies; C.hoff = (hcopies > 1) ? lane : 0;
+  C.hmul = hcopies; C.hoff = lane & (hcopies - 1);       // (hcopies: a power of two)
   uint8_t *s_stab = smem + pl.off_stab, *s_ptab = smem + pl.off_ptab, *s_mutab = smem + pl.off_mutab;
   T *s_s2bin = reinterpret_cast<T *>(smem + pl.off_s2bin), *s_pbin = reinterpret_cast<T *>(smem + pl.off_pbin);
   int4 *s_rows = reinterpret_cast<int4 *>(smem + pl.off_rows);
@@ -979,7 +981,7 @@ __global__ void __launch_bounds__(BlockShape<T>::kThreads, 1) count_kernel(const
   __syncthreads();
   FastCtx F;
   F.hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
-  F.hstride = 8u * (unsigned int) hcopies; F.hlane = (hcopies > 1) ? 8u * (unsigned int) lane : 0u;
+  F.hstride = 8u * (unsigned int) hcopies; F.hlane = 8u * (unsigned int) (lane & (hcopies - 1));
   F.stab_s = (unsigned int) __cvta_generic_to_shared(s_stab);
   F.ptab_s = (unsigned int) __cvta_generic_to_shared(s_ptab);
   F.mutab_s = (unsigned int) __cvta_generic_to_shared(s_mutab);

@@ -118,7 +118,8 @@ __global__ void __launch_bounds__(kClThreads, 1) count_kernel_cl(const __grid_co
     if (mx + need <= P.qdepth - 1) return mx;
     const int rounds = min((mx - keep + 3) & ~3, 32);
     if (rounds <= 0) return 0;
-    drain_fast<T, BIN, BOX, false, ARITH, NW>(P, C, F, Q, rounds);
+    __syncwarp();               // the columns rotate between the lanes: pushes of other lanes must be visible to whoever pops
+    drain_fast<T, BIN, BOX, false, ARITH, NW>(P, C, F, Q, rounds);      // (ends with __syncwarp())
     return max(mx - rounds, 0);
   };
 

@@ -84,7 +84,7 @@ __global__ void __launch_bounds__(kDfThreads, 1) count_kernel_df(const __grid_co
   const unsigned int qbase = (unsigned int) __cvta_generic_to_shared(wbase + pl.o_stack) + 8u * (unsigned int) lane;
   unsigned int qtop = qbase;
   const unsigned int hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
-  const unsigned int hstride = 8u * (unsigned int) hcopies, hlane = (hcopies > 1) ? 8u * (unsigned int) lane : 0u;
+  const unsigned int hstride = 8u * (unsigned int) hcopies, hlane = 8u * (unsigned int) (lane & (hcopies - 1));
   const unsigned int hist_adj = hist_s + (WT ? hlane : 0u) - (WT ? hstride : 4u) * P.fb_bias;        // base of the biased fast bins
   const unsigned int dump = hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (unsigned int) lane;
   // exact context of the flagged pairs: tables through global memory (a few pairs per thousand)

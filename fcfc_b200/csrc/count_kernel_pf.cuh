@@ -93,7 +93,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   BlockCtx<T> C;
   C.hist_u = SMEMHIST ? reinterpret_cast<unsigned int *>(smem + pl.off_hist) : reinterpret_cast<unsigned int *>(P.ghist_i);
   C.hist_d = SMEMHIST ? reinterpret_cast<double *>(smem + pl.off_hist) : P.ghist_d;
-  C.hmul = hcopies; C.hoff = (hcopies > 1) ? lane : 0;
+  C.hmul = hcopies; C.hoff = lane & (hcopies - 1);       // (hcopies: a power of two)
   uint8_t *s_stab = smem + pl.off_stab, *s_ptab = smem + pl.off_ptab, *s_mutab = smem + pl.off_mutab;
   T *s_s2bin = reinterpret_cast<T *>(smem + pl.off_s2bin), *s_pbin = reinterpret_cast<T *>(smem + pl.off_pbin);
   int4 *s_rows = reinterpret_cast<int4 *>(smem + pl.off_rows);
@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   const unsigned int stage_d_s = (unsigned int) __cvta_generic_to_shared(stage_d);
   const unsigned int stage_f_s = (unsigned int) __cvta_generic_to_shared(wbase + pl.o_stage_f);
   const unsigned int hist_s = (unsigned int) __cvta_generic_to_shared(smem + pl.off_hist);
-  const unsigned int hstride = 8u * (unsigned int) hcopies, hlane = (hcopies > 1) ? 8u * (unsigned int) lane : 0u;
+  const unsigned int hstride = 8u * (unsigned int) hcopies, hlane = 8u * (unsigned int) (lane & (hcopies - 1));
   const unsigned int dump = hist_s + 4u * (unsigned int) (P.ntot + P.ns + 1) + 4u * (unsigned int) lane;
   // binning path of the exact pass (warp-uniform): computed bins + exact re-binning of flagged pairs, or bin_entry
   const bool fast = !GENERIC && SMEMHIST && BIN != BIN_SPI && P.stab_is_sqrt && (BIN != BIN_SMU || P.mu_is_sqrt);

@@ -1064,9 +1064,14 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     double d2lim = 0, s1sq = 0, flagged = 0;
     const double cs_max = std::max(g.cs[0], std::max(g.cs[1], g.cs[2]));
     if (fcfc_gpu_df_budget(ns, bintype == BIN_SMU ? nmu : 1, s2max, cs_max, &ks, &km, &d2lim, &s1sq, &flagged)) {
-      dpl = withwt ? make_df_plan<true>((int) ntot, ns, (int) rows.size(), hist_copies) : make_df_plan<false>((int) ntot, ns, (int) rows.size(), 1);
+      // (its stacks are small: spare shared memory goes to copies of the weighted histogram, as for the pre-filter kernel below)
+      int dcopies = hist_copies;
+      for (int hc = (withwt && !opt.no_hist_copies) ? 8 : 1; hc > hist_copies; hc >>= 1)
+        if (make_df_plan<true>((int) ntot, ns, (int) rows.size(), hc).total + 1024 <= smem_max) { dcopies = hc; break; }
+      dpl = withwt ? make_df_plan<true>((int) ntot, ns, (int) rows.size(), dcopies) : make_df_plan<false>((int) ntot, ns, (int) rows.size(), 1);
       if (dpl.total + 1024 <= smem_max) {
         use_df = true;
+        if (withwt) P.hist_copies = dcopies;
         P.fb_sscale = (float) std::ldexp(1.0, ks); P.fb_mscale = (float) std::ldexp((double) nmu, km);
         P.fb_smask = (1u << ks) - 4u; P.fb_mmask = (1u << km) - 2u; P.fb_sshift = (unsigned) ks; P.fb_mshift = (unsigned) km;
         P.fb_smul = 1u << (32 - ks); P.fb_mmul = 1u << (32 - km);
@@ -1087,13 +1092,19 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
     for (int d = 0; d < 3; d++) M = std::max(M, std::max(std::fabs(lo[d]), std::fabs(hi[d])) + (b->periodic ? b->bsize[d] : 0.0));
     const int mode = fcfc_gpu_prefilter_limits(b->periodic, bintype, s2max, pmax, M, std::max(c1->smax, c2->smax), std::min(c1->smin, c2->smin), lim);
     if (mode) {
+      // this kernel has no stacks: what shared memory is left goes to copies of the weighted histogram (lane l adds to copy
+      // l mod copies), which thins out the collisions of the CAS-based FP64 atomics inside a warp
       for (int tg = tables_unused ? 1 : 0; tg < 2 && !use_pf; tg++) {
-        ppl = withwt ? make_pf_plan<true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, hist_copies, kR)
-                     : make_pf_plan<false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, 1, kR);
-        if (ppl.total + 1024 <= smem_max) {
-          use_pf = true;
-          P.tabs_global = tg;
-          v.generic = generic || opt.force_generic || (tg && !tables_unused);
+        for (int hc = (withwt && !opt.no_hist_copies) ? 8 : 1; hc >= 1 && !use_pf; hc >>= 1) {
+          const int copies = std::max(hc, hist_copies);
+          ppl = withwt ? make_pf_plan<true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, copies, kR)
+                       : make_pf_plan<false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, 1, kR);
+          if (ppl.total + 1024 <= smem_max) {
+            use_pf = true;
+            P.tabs_global = tg;
+            P.hist_copies = withwt ? copies : 1;
+            v.generic = generic || opt.force_generic || (tg && !tables_unused);
+          }
         }
       }
       if (use_pf) { P.pf_d2lim = (float) lim[0]; P.pf_plim = (float) lim[1]; P.pf_s2lim = (float) lim[2]; }
