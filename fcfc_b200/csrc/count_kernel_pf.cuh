@@ -27,7 +27,7 @@
 namespace fcfc {
 
 #ifndef FCFC_PF_WARPS
-#define FCFC_PF_WARPS 20
+#define FCFC_PF_WARPS 24
 #endif
 constexpr int kPfWarps = FCFC_PF_WARPS, kPfThreads = kPfWarps * 32;
 
