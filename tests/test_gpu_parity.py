@@ -138,6 +138,24 @@ def test_classified_staging_vs_plain(gpu, kw, arith, origin, tuned):
         np.testing.assert_array_equal(on["DR"], oracle.count(ob, pa, pb))
 
 
+@pytest.mark.parametrize("prec", ["float", "double"])
+@pytest.mark.parametrize("kw", [dict(bintype=1, smax=49.0, ds=3.5, nmu=15), dict(bintype=0, smax=49.5, ds=1.5)])
+def test_reach_of_almost_half_the_box(gpu, prec, kw):
+    """Maximum separation just below half the box (the reference's own limit): every cell is a neighbour of every other
+    through some periodic image, a stencil row wraps around and meets itself, image shifts change from row to row -- the
+    bookkeeping the classified staging has to flush its rings for.  12k points, auto and cross, against the oracle."""
+    L = 100.0
+    a = box_catalog(9000, L, 81, weights=False)
+    c = clustered_box_catalog(3000, L, 82)[:3]
+    a = tuple(np.concatenate([u, v]) for u, v in zip(a, c))
+    b = box_catalog(5000, L, 83, weights=False)
+    got = gpu_counts(gpu, dict(box=L, **kw), True, prec, [a, b], ["DD", "DR"], False, arith=1)
+    ob = oracle.setup(prec=prec[0], periodic=True, arith=1, box=L, **kw)
+    pa, pb = oracle.preprocess(ob, a), oracle.preprocess(ob, b)
+    np.testing.assert_array_equal(got["DD"], oracle.count(ob, pa))
+    np.testing.assert_array_equal(got["DR"], oracle.count(ob, pa, pb))
+
+
 @pytest.mark.parametrize("kw,withwt", [(dict(bintype=2, smax=24.0, ds=2.0, pmin=0.0, pmax=60.0, dpi=2.0), True),
                                        (dict(bintype=2, smax=40.0, ds=2.0, pmin=0.0, pmax=30.0, dpi=1.0), False),
                                        (dict(bintype=1, smax=60.0, ds=3.0, nmu=30), True)])

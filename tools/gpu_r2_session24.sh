@@ -1,11 +1,6 @@
 #!/bin/bash
-# gpurun script: warps per block of the pre-filter kernel (16 / 20 / 24) on the survey (s_perp,pi) weighted counts.
+# gpurun script: warps per block of the double-precision float-speed kernel (20 / 24 / 28) on the bench workload.
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-T0=$(date +%s); el() { echo "[$(( $(date +%s) - T0 )) s] $*" | tee -a $O/s24_timeline.log; }
-for v in main pf16 pf24; do
-  if [ $v = main ]; then unset FCFC_B200_LIB; else export FCFC_B200_LIB=$PWD/fcfc_b200/_variants/$v/libfcfc_b200.so; fi
-  FCFC_TS_BINTYPES=2,1 FCFC_TS_WEIGHTED_ONLY=1 timeout 300 python tools/time_survey.py 200000 2000000 double > $O/s24_svy_$v.log 2>&1; el "survey $v rc=$?"; cat $O/s24_svy_$v.log | cut -c1-220 | tee -a $O/s24_timeline.log
-done
-el done
+timeout 600 python tools/time_c2_double.py fcfc_b200/libfcfc_b200.so fcfc_b200/_variants/df20/libfcfc_b200.so fcfc_b200/_variants/df28/libfcfc_b200.so 2>&1 | tee $O/s24_df_warps.log
