@@ -869,7 +869,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   const int stab_is_sqrt = (b->tabtype == FCFC_GPU_TAB_INT && s2bin[0] == 0) ? table_is_sqrt(b->stab, b->swidth, nstab) : 0;
   // counts that will take the classified-staging kernel (count_kernel_cl.cuh; the shared-memory plan confirms it below)
   // get tiles of 32 kClR points: fewer registers for the tile, measured 2 % faster on the bench workload
-  const bool cl_candidate = is_float && !withwt && bintype != BIN_SPI && b->periodic && s2bin[0] == 0 && b->swidth == 0 &&
+  const bool cl_candidate = is_float && !withwt && bintype != BIN_SPI && (b->periodic || bintype == BIN_ISO) && s2bin[0] == 0 && b->swidth == 0 &&
                             b->tabtype == FCFC_GPU_TAB_INT && stab_is_sqrt && (bintype == BIN_ISO || mu_is_sqrt) &&
                             !opt.no_table_math && !opt.no_dense && !opt.no_classify && !opt.force_generic && !opt.global_hist;
   const int tile = 32 * (cl_candidate ? kClR : kR);    // (tiles of 96 points were measured for count_kernel_df too: 468.5 -> 474.6 ms)
@@ -1115,7 +1115,11 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   bool use_cl = false;
   ClPlan cpl{};
   if constexpr (is_float) {
-    if (dense && !opt.no_classify) {
+    // (box (s,mu) / isotropic: the counts that also qualify for the dense cells of count_kernel; survey isotropic: same kernel
+    // without image shifts)
+    const bool cl_ok = !withwt && bintype != BIN_SPI && (b->periodic || bintype == BIN_ISO) && !v.generic && v.smem_hist &&
+                       P.stab_is_sqrt && (bintype == BIN_ISO || P.mu_is_sqrt) && !opt.no_dense;
+    if (cl_ok && !opt.no_classify) {
       int cdepth = 0;
       for (int d = std::min(qdepth_max, 64) & ~3; d >= 12 && !cdepth; d -= 4) {
         cpl = make_cl_plan((int) ntot, ns, (int) rows.size(), qwords, d);

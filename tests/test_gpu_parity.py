@@ -138,6 +138,30 @@ def test_classified_staging_vs_plain(gpu, kw, arith, origin, tuned):
         np.testing.assert_array_equal(on["DR"], oracle.count(ob, pa, pb))
 
 
+@pytest.mark.parametrize("arith", [0, 1])
+def test_survey_isotropic_float_classified(gpu, arith, tuned):
+    """Survey isotropic counts in single precision take count_kernel_cl as well (no image shifts: the rings are only flushed at
+    the end of a work item); against the plain kernel and the oracle, auto and cross."""
+    D, R = survey_catalog(20000, 91)[:3], survey_catalog(30000, 92)[:3]
+    kw = dict(bintype=0, smax=150.0, ds=5.0)
+    bins = gpu.Bins(periodic=False, prec="float", arith=arith, **kw)
+    gd, gr = gpu.Catalog(*D, bins=bins), gpu.Catalog(*R, bins=bins)
+    on = {}
+    for name, a, c in (("DD", gd, None), ("DR", gd, gr)):
+        on[name] = gpu.count_pairs(a, c, bins)
+        st = gpu.stats()
+        assert st["classified"] == 1 and st["pair_evals_computed"] < st["pair_evals"]
+    tuned("no_classify", 1)
+    for name, a, c in (("DD", gd, None), ("DR", gd, gr)):
+        np.testing.assert_array_equal(on[name], gpu.count_pairs(a, c, bins))
+        assert gpu.stats()["classified"] == 0
+    gd.destroy(); gr.destroy()
+    ob = oracle.setup(prec="f", periodic=False, arith=arith, **kw)
+    pd, pr = oracle.preprocess(ob, D), oracle.preprocess(ob, R)
+    np.testing.assert_array_equal(on["DD"], oracle.count(ob, pd))
+    np.testing.assert_array_equal(on["DR"], oracle.count(ob, pd, pr))
+
+
 @pytest.mark.parametrize("prec", ["float", "double"])
 @pytest.mark.parametrize("kw", [dict(bintype=1, smax=49.0, ds=3.5, nmu=15), dict(bintype=0, smax=49.5, ds=1.5)])
 def test_reach_of_almost_half_the_box(gpu, prec, kw):
