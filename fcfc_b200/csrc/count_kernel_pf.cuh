@@ -29,13 +29,16 @@ namespace fcfc {
 #ifndef FCFC_PF_WARPS
 #define FCFC_PF_WARPS 24
 #endif
-constexpr int kPfWarps = FCFC_PF_WARPS, kPfThreads = kPfWarps * 32;
+// Warps per block (one block per SM).  Measured on survey counts (profiles/dense_block_experiments_r2.log): 16 / 20 / 24 / 28
+// warps give 26.6 / 24.0 / 21.9 / 20.7 ms for (s_perp,pi) -- its exact pass is a chain of dependent FP64 operations and a
+// division, bound by latency -- and 503.6 / 457.5 / 432.5 / 436.4 ms for (s,mu).
+__host__ __device__ constexpr int pf_warps(int bintype, bool box) { return (bintype == BIN_SPI && !box) ? 28 : FCFC_PF_WARPS; }
 
 struct PfPlan { int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_misc, off_warp, per_warp, o_stage_d, o_wbuf, o_stage_f, o_box, o_clist, total; };
 
 template <bool WT>
 __host__ __device__ inline PfPlan make_pf_plan(int ntot, int nstab_bytes, int nptab_bytes, int nmutab_bytes, int ns, int np, int nrows,
-                                               bool smem_hist, bool tabs_global, int hist_copies, int rmax) {
+                                               bool smem_hist, bool tabs_global, int hist_copies, int warps) {
   PfPlan p;
   int o = 0;
   auto al = [](int v) { return (v + 15) & ~15; };
@@ -56,9 +59,8 @@ __host__ __device__ inline PfPlan make_pf_plan(int ntot, int nstab_bytes, int np
   p.o_stage_f = w; w += 1024;                   // float copies: 32 pairs x (x0 x1 y0 y1) | 32 pairs x (z0 z1 s0 s1)
   p.o_box = w; w += 48;                         // the tile for the classification: (cx, cy, cz, R) (hx, hy, hz, -) (s_min, s_max, -, -)
   p.o_clist = w; w += 1024 * 2;                 // candidate codes of one primary slot: (lane << 5) | secondary, at most 32 x 32
-  (void) rmax;
   p.per_warp = w;
-  p.total = o + kPfWarps * w;
+  p.total = o + warps * w;
   return p;
 }
 
@@ -78,7 +80,8 @@ __device__ __noinline__ void pf_fix_pair(const CountParams<double> &P, unsigned 
 }
 
 template <int BIN, bool BOX, bool WT, int ARITH, bool GENERIC, bool SMEMHIST, int RMAX>
-__global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_constant__ CountParams<double> P) {
+__global__ void __launch_bounds__(pf_warps(BIN, BOX) * 32, 1) count_kernel_pf(const __grid_constant__ CountParams<double> P) {
+  constexpr int kPfWarps = pf_warps(BIN, BOX), kPfThreads = kPfWarps * 32;
   using T = double;
   using A = Ar<double>;
   extern __shared__ __align__(16) unsigned char smem[];
@@ -89,7 +92,7 @@ __global__ void __launch_bounds__(kPfThreads, 1) count_kernel_pf(const __grid_co
   const int nmutab = (BIN == BIN_SMU) ? P.nmu2 : 0;
   const int hcopies = (WT && SMEMHIST) ? P.hist_copies : 1;
   const PfPlan pl = make_pf_plan<WT>(P.ntot, P.nstab * (P.swidth ? 2 : 1), P.nptab * (P.pwidth ? 2 : 1), nmutab, P.ns, P.np, P.nrows,
-                                     SMEMHIST, P.tabs_global != 0, hcopies, RMAX);
+                                     SMEMHIST, P.tabs_global != 0, hcopies, kPfWarps);
   BlockCtx<T> C;
   C.hist_u = SMEMHIST ? reinterpret_cast<unsigned int *>(smem + pl.off_hist) : reinterpret_cast<unsigned int *>(P.ghist_i);
   C.hist_d = SMEMHIST ? reinterpret_cast<double *>(smem + pl.off_hist) : P.ghist_d;

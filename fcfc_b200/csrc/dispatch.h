@@ -67,7 +67,7 @@ static inline cudaError_t launch_count_pf(const Variant &v, const CountParams<do
     auto kern = count_kernel_pf<BIN, BOX, WT, ARITH, GENERIC, true, kR>;                                 \
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes); \
     if (e != cudaSuccess) return e;                                                                      \
-    kern<<<nblocks, kPfThreads, smem_bytes>>>(P);                                                        \
+    kern<<<nblocks, pf_warps(BIN, BOX) * 32, smem_bytes>>>(P);                                                        \
     return cudaGetLastError();                                                                           \
   }
 

@@ -1097,8 +1097,8 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
       for (int tg = tables_unused ? 1 : 0; tg < 2 && !use_pf; tg++) {
         for (int hc = (withwt && !opt.no_hist_copies) ? 8 : 1; hc >= 1 && !use_pf; hc >>= 1) {
           const int copies = std::max(hc, hist_copies);
-          ppl = withwt ? make_pf_plan<true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, copies, kR)
-                       : make_pf_plan<false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, 1, kR);
+          ppl = withwt ? make_pf_plan<true>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, copies, pf_warps(bintype, b->periodic != 0))
+                       : make_pf_plan<false>((int) ntot, (int) sz_stab, (int) sz_ptab, nmutab, ns, np, (int) rows.size(), true, tg != 0, 1, pf_warps(bintype, b->periodic != 0));
           if (ppl.total + 1024 <= smem_max) {
             use_pf = true;
             P.tabs_global = tg;
@@ -1142,7 +1142,7 @@ static int count_impl(DevCat *c1, DevCat *c2, const fcfc_gpu_bins *b, int isauto
   g_stats.prefilter = use_df ? 2 : (use_pf ? 1 : 0);
   cudaEventRecord(evs[1]);
   const int my_items = (S1.nitem * nsplit - part + nparts - 1) / nparts;
-  const int warps_blk = use_df ? kDfWarps : (use_pf ? kPfWarps : (use_cl ? kClWarps : BlockShape<T>::kWarps));
+  const int warps_blk = use_df ? kDfWarps : (use_pf ? pf_warps(bintype, b->periodic != 0) : (use_cl ? kClWarps : BlockShape<T>::kWarps));
   const int nblocks = std::max(1, std::min(g_ctx.sm_count, (my_items + warps_blk - 1) / warps_blk));
   cudaError_t le;
   if constexpr (!is_float) le = use_df ? launch_count_df(v, P, nblocks, dpl.total)
