@@ -29,10 +29,13 @@ namespace fcfc {
 #ifndef FCFC_PF_WARPS
 #define FCFC_PF_WARPS 24
 #endif
+#ifndef FCFC_PF_WARPS_SPI
+#define FCFC_PF_WARPS_SPI 28
+#endif
 // Warps per block (one block per SM).  Measured on survey counts (profiles/dense_block_experiments_r2.log): 16 / 20 / 24 / 28
 // warps give 26.6 / 24.0 / 21.9 / 20.7 ms for (s_perp,pi) -- its exact pass is a chain of dependent FP64 operations and a
 // division, bound by latency -- and 503.6 / 457.5 / 432.5 / 436.4 ms for (s,mu).
-__host__ __device__ constexpr int pf_warps(int bintype, bool box) { return (bintype == BIN_SPI && !box) ? 28 : FCFC_PF_WARPS; }
+__host__ __device__ constexpr int pf_warps(int bintype, bool box) { return (bintype == BIN_SPI && !box) ? FCFC_PF_WARPS_SPI : FCFC_PF_WARPS; }
 
 struct PfPlan { int off_hist, off_stab, off_ptab, off_mutab, off_s2bin, off_pbin, off_rows, off_misc, off_warp, per_warp, o_stage_d, o_wbuf, o_stage_f, o_box, o_clist, total; };
 

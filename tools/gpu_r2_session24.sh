@@ -1,6 +1,9 @@
 #!/bin/bash
-# gpurun script: warps per block of the double-precision float-speed kernel (20 / 24 / 28) on the bench workload.
+# gpurun script: survey (s_perp,pi) variants of the pre-filter kernel at 28 / 32 warps.
 set -u
 cd "$(dirname "$0")/.."
 O=gpurun_out; mkdir -p $O
-timeout 600 python tools/time_c2_double.py fcfc_b200/libfcfc_b200.so fcfc_b200/_variants/df20/libfcfc_b200.so fcfc_b200/_variants/df28/libfcfc_b200.so 2>&1 | tee $O/s24_df_warps.log
+for v in main pf32; do
+  if [ $v = main ]; then unset FCFC_B200_LIB; else export FCFC_B200_LIB=$PWD/fcfc_b200/_variants/$v/libfcfc_b200.so; fi
+  FCFC_TS_BINTYPES=2 FCFC_TS_WEIGHTED_ONLY=1 timeout 300 python tools/time_survey.py 200000 2000000 double 2>&1 | cut -c1-220
+done
