@@ -1,7 +1,7 @@
 """Golden vectors of the BASELINE configs at their real size, from the compiled, unmodified reference (oracle/_ref).
 
 Run in the build container (where /root/reference exists and `make -C oracle` has been run):
-    python tests/golden/make_golden_fullsize.py [c1] [c2] [c4s]
+    python tests/golden/make_golden_fullsize.py [c1] [c2] [c4s] [c3]
 It takes tens of minutes of CPU time (the 10^7-point (s,mu) count is ~2x10^11 in-range pairs per run), which is why
 the outputs are committed as fixtures (fullsize_*.npz) instead of being recomputed by the tests:
 
@@ -9,6 +9,8 @@ the outputs are committed as fixtures (fullsize_*.npz) instead of being recomput
   c2   BASELINE configs[1]: 10^7 uniform points, L = 2000, xi(s,mu) 40 x 120, DD (bench.py workload c2_box_smu_1e7,
        the headline bench workload: bench.py checks its own step against these counts)
   c4s  a 2x10^6-point clustered (s,mu) box, the small-scale twin of configs[3]
+  c3   BASELINE configs[2]: survey, 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) (bench.py workload
+       c3_svy_spi_wt_2e6_2e7; only when named: it is not in the default list)
 
 For each: the reference's double AVX-512 build (k-d tree) -- which the survey found identical to the scalar double
 build and to the ball tree -- and the float AVX-512 / float scalar builds with both trees, whose mutual differences
@@ -39,6 +41,24 @@ JOBS = {
 }
 
 
+def survey_job():
+    """c3: BASELINE configs[2], 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) 20 x 80 bins, the reference's
+    default (double, AVX-512) build (bench.py workload c3_svy_spi_wt_2e6_2e7: bench.py checks its own step against these sums)."""
+    wl = bench.SURVEY_WORKLOADS["c3_svy_spi_wt_2e6_2e7"]
+    threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
+    D, R = bench.make_survey(wl["nd"], 1), bench.make_survey(wl["nr"], 2)
+    out = {"input_sha256": np.array(checksum(D + R)), "nd": np.array(wl["nd"]), "nr": np.array(wl["nr"]), "workload": np.array("c3_svy_spi_wt_2e6_2e7")}
+    t0 = time.time()
+    r = refdrv.run_reference([tuple(D), tuple(R)], periodic=False, prec="dbl", isa="avx512", pairs=["DD", "DR", "RR"], threads=threads,
+                             bintype=2, smin=0.0, smax=wl["smax"], ds=wl["ds"], pmin=0.0, pmax=wl["pmax"], dpi=wl["dpi"], timeout=6 * 3600)
+    for k, p in enumerate(["DD", "DR", "RR"]):
+        out[f"dbl_avx512_kd_{p}"] = r.pairs[k].cnt
+        out[f"dbl_avx512_kd_{p}_seconds"] = np.array(r.pairs[k].t_count)
+        print("c3", p, f"weighted sum {r.pairs[k].cnt.sum():.10g}, count_pairs {r.pairs[k].t_count:.1f} s on {threads} threads", flush=True)
+    print("c3 wall", f"{time.time() - t0:.1f} s", flush=True)
+    np.savez_compressed(os.path.join(HERE, "fullsize_c3.npz"), **out)
+
+
 def checksum(cols):
     h = hashlib.sha256()
     for a in cols:
@@ -50,6 +70,9 @@ def main():
     names = sys.argv[1:] or list(JOBS)
     threads = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     for name in names:
+        if name == "c3":
+            survey_job()
+            continue
         job = JOBS[name]
         wl = bench.WORKLOADS[job["workload"]]
         n = job["n"] or wl["n"]

@@ -4,6 +4,7 @@ tests/golden/fullsize_*.npz hold the raw count_pairs output of the unmodified re
   c1   configs[0]: 10^6 uniform points, L = 1000, xi(s), 40 bins
   c2   configs[1]: 10^7 uniform points, L = 2000, xi(s,mu), 40 x 120 bins   (the bench workload)
   c4s  2x10^6 clustered points, xi(s,mu): the small-scale twin of configs[3]
+  c3   configs[2]: survey, 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) 20 x 80 bins (double AVX-512 build)
 generated once by tests/golden/make_golden_fullsize.py (tens of CPU minutes, hence fixtures).
 
 Bars (north_star): double precision -- the reference's default build -- bit-exact in BOTH evaluation orders against the
@@ -98,3 +99,23 @@ def test_gpu_float_within_reference_spread_at_full_size(gpu, name, arith):
     assert abs(int(got.sum()) - int(ref.sum())) <= max(4, 2 * int(np.abs(np.diff([int(v.sum()) for v in float_refs(g).values()])).max()))
     # and against double: float rounding moves a pair across an s or mu bin edge with probability ~1e-5
     assert np.abs(got - g["dbl_avx512_kd_DD"]).sum() <= 1e-4 * got.sum()
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not os.path.exists(os.path.join(os.path.dirname(__file__), "golden", "fullsize_c3.npz")), reason="fullsize_c3.npz not generated")
+def test_gpu_survey_weighted_equals_reference_at_full_size(gpu):
+    """BASELINE configs[2] at its real size: 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) 20 x 80 bins,
+    double precision, against the sums of the reference's default (double, AVX-512) build for the same catalogues:
+    1e-12 relative per bin, identical empty bins."""
+    import bench
+    wl = bench.SURVEY_WORKLOADS["c3_svy_spi_wt_2e6_2e7"]
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "fullsize_c3.npz"))
+    D, R = bench.make_survey(wl["nd"], 1), bench.make_survey(wl["nr"], 2)
+    b = gpu.Bins(periodic=False, prec="double", bintype=2, smin=0.0, smax=wl["smax"], ds=wl["ds"], pmin=0.0, pmax=wl["pmax"], dpi=wl["dpi"])
+    gd, gr = gpu.Catalog(*D, bins=b), gpu.Catalog(*R, bins=b)
+    for name, a, c in (("DD", gd, None), ("DR", gd, gr), ("RR", gr, None)):
+        got = gpu.count_pairs(a, c, b, withwt=True)
+        ref = g[f"dbl_avx512_kd_{name}"]
+        np.testing.assert_array_equal(got == 0, ref == 0)
+        np.testing.assert_allclose(got, ref, rtol=1e-12, atol=0)
+    gd.destroy(); gr.destroy()
