@@ -1,7 +1,7 @@
 """Golden vectors of the BASELINE configs at their real size, from the compiled, unmodified reference (oracle/_ref).
 
 Run in the build container (where /root/reference exists and `make -C oracle` has been run):
-    python tests/golden/make_golden_fullsize.py [c1] [c2] [c4s] [c3]
+    python tests/golden/make_golden_fullsize.py [c1] [c2] [c4s] [c4] [c3]
 It takes tens of minutes of CPU time (the 10^7-point (s,mu) count is ~2x10^11 in-range pairs per run), which is why
 the outputs are committed as fixtures (fullsize_*.npz) instead of being recomputed by the tests:
 
@@ -9,6 +9,8 @@ the outputs are committed as fixtures (fullsize_*.npz) instead of being recomput
   c2   BASELINE configs[1]: 10^7 uniform points, L = 2000, xi(s,mu) 40 x 120, DD (bench.py workload c2_box_smu_1e7,
        the headline bench workload: bench.py checks its own step against these counts)
   c4s  a 2x10^6-point clustered (s,mu) box, the small-scale twin of configs[3]
+  c4   the clustered (s,mu) box at the single-GPU size of configs[3]: 10^7 points, L = 2000 (bench.py workload
+       c4_box_smu_clustered_1e7)
   c3   BASELINE configs[2]: survey, 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) (bench.py workload
        c3_svy_spi_wt_2e6_2e7; only when named: it is not in the default list)
 
@@ -38,6 +40,8 @@ JOBS = {
                runs=[("dbl", "avx512", 0), ("flt", "avx512", 0), ("flt", "avx512", 1), ("flt", "scalar", 0)]),
     "c4s": dict(workload="c4_box_smu_clustered_1e7", n=2_000_000, box=1169.607095285,
                 runs=[("dbl", "avx512", 0), ("flt", "avx512", 0), ("flt", "avx512", 1), ("flt", "scalar", 0)]),
+    "c4": dict(workload="c4_box_smu_clustered_1e7", n=None,
+               runs=[("dbl", "avx512", 0), ("flt", "avx512", 0), ("flt", "avx512", 1), ("flt", "scalar", 0)]),
 }
 
 

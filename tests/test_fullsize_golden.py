@@ -4,6 +4,7 @@ tests/golden/fullsize_*.npz hold the raw count_pairs output of the unmodified re
   c1   configs[0]: 10^6 uniform points, L = 1000, xi(s), 40 bins
   c2   configs[1]: 10^7 uniform points, L = 2000, xi(s,mu), 40 x 120 bins   (the bench workload)
   c4s  2x10^6 clustered points, xi(s,mu): the small-scale twin of configs[3]
+  c4   10^7 clustered points, L = 2000, xi(s,mu): configs[3] at its single-GPU size (bench.py workload c4_box_smu_clustered_1e7)
   c3   configs[2]: survey, 2x10^6 data + 2x10^7 randoms, weighted DD + DR + RR, xi(s_perp,pi) 20 x 80 bins (double AVX-512 build)
 generated once by tests/golden/make_golden_fullsize.py (tens of CPU minutes, hence fixtures).
 
@@ -19,7 +20,7 @@ import pytest
 import bench
 from conftest import GOLDEN
 
-NAMES = ["c1", "c2", "c4s"]
+NAMES = ["c1", "c2", "c4s", "c4"]
 
 
 def load(name):
@@ -46,7 +47,7 @@ def test_fixture_facts(name):
     assert len(fl) >= 2
     tot = int(dbl[0].sum())
     n, L = int(g["n"]), float(g["box"])
-    if name != "c4s":           # uniform catalogues: the analytic pair count, 5 sigma (+ the mu = 1 pairs dropped by (s,mu))
+    if name not in ("c4s", "c4"):   # uniform catalogues: the analytic pair count, 5 sigma (+ the mu = 1 pairs dropped by (s,mu))
         expect = 0.5 * n * (n - 1) * (4.0 / 3.0 * np.pi * 200.0 ** 3) / L ** 3
         assert abs(tot - expect) < 5 * np.sqrt(expect) + 1e-5 * expect
     for v in fl.values():
