@@ -8,7 +8,7 @@
 // that is fastest for the bench workload it hands the pair loop 2.06 candidates per pair in range, and only a third of
 // the accepted pairs sit in cells that are entirely in range.  Here the lane that stages a secondary point also tests it
 // against the bounding box of the tile's primaries (centre c, half-widths h, 18 FP32 instructions per staged point,
-// i.e. per <= 128 pair evaluations):
+// i.e. per <= 96 pair evaluations):
 //
 //   * nearest point of the box farther than the maximum separation  -> the point is dropped (no pair can be in range);
 //   * farthest corner of the box within the maximum separation      -> "dense" point: every pair is in range, the pair
