@@ -183,7 +183,8 @@ __global__ void __launch_bounds__(pf_warps(BIN, BOX) * 32, 1) count_kernel_pf(co
       if (lane == 0) {
         const float hx = 0.5f * (hi[0] - lo[0]), hy = 0.5f * (hi[1] - lo[1]), hz = 0.5f * (hi[2] - lo[2]);
         s_box[0] = 0.5f * (lo[0] + hi[0]); s_box[1] = 0.5f * (lo[1] + hi[1]); s_box[2] = 0.5f * (lo[2] + hi[2]);
-        s_box[3] = sqrtf(hx * hx + hy * hy + hz * hz) * 1.001f + 1e-3f * fmaxf(fabsf(hi[0]), fmaxf(fabsf(hi[1]), fabsf(hi[2]))) * 1e-3f;
+        const float cmax = fmaxf(fmaxf(fmaxf(fabsf(lo[0]), fabsf(hi[0])), fmaxf(fabsf(lo[1]), fabsf(hi[1]))), fmaxf(fabsf(lo[2]), fabsf(hi[2])));
+        s_box[3] = sqrtf(hx * hx + hy * hy + hz * hz) * 1.001f + 1e-6f * cmax;        // half-diagonal + a few ulps of the largest coordinate
         s_box[4] = hx; s_box[5] = hy; s_box[6] = hz;
         s_box[8] = smn * 0.999999f; s_box[9] = smx * 1.000001f;
       }

@@ -104,7 +104,7 @@ def test_survey_cylinder_classification_is_safe():
         ps = (prim ** 2).sum(1)
         lo, hi = pf.min(0), pf.max(0)
         h = (f32(0.5) * (hi - lo)).astype(f32); c = (f32(0.5) * (lo + hi)).astype(f32)
-        R = f32(np.sqrt(f32(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]))) * f32(1.001) + f32(1e-3) * np.abs(hi).max().astype(f32) * f32(1e-3)
+        R = f32(np.sqrt(f32(h[0] * h[0] + h[1] * h[1] + h[2] * h[2]))) * f32(1.001) + f32(1e-6) * np.maximum(np.abs(lo), np.abs(hi)).max().astype(f32)
         smn, smx = f32(ps.min()) * f32(0.999999), f32(ps.max()) * f32(1.000001)
         f_d2lim = f32((s2max + p2max) * (1 + 1e-5))                                  # (the filter's padded sphere, never below the exact one)
         f_s2cl, f_p2cl = f32(s2max) * f32(1.001), f32(p2max) * f32(1.001)
