@@ -69,6 +69,14 @@ def lib():
         L.fcfc_gpu_catalog_size.argtypes = [C.c_void_p]
         L.fcfc_gpu_catalog_wsum.restype = C.c_double
         L.fcfc_gpu_catalog_wsum.argtypes = [C.c_void_p]
+        L.fcfc_gpu_catalog_stream_begin.restype = C.c_void_p
+        L.fcfc_gpu_catalog_stream_begin.argtypes = [C.c_size_t, C.c_int, C.c_int]
+        L.fcfc_gpu_catalog_stream_append.argtypes = [C.c_void_p] * 5 + [C.c_size_t]
+        L.fcfc_gpu_catalog_stream_size.restype = C.c_size_t
+        L.fcfc_gpu_catalog_stream_size.argtypes = [C.c_void_p]
+        L.fcfc_gpu_catalog_stream_finish.restype = C.c_void_p
+        L.fcfc_gpu_catalog_stream_finish.argtypes = [C.c_void_p, C.c_double, C.c_int]
+        L.fcfc_gpu_catalog_stream_abort.argtypes = [C.c_void_p]
         L.fcfc_gpu_count_partial.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_CBins), C.c_int, C.c_int, C.c_int,
                                              C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         L.fcfc_gpu_count.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(_CBins), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
@@ -84,6 +92,8 @@ def lib():
         L.fcfc_gpu_measure_fp32_peak.argtypes = [C.POINTER(C.c_double)]
         L.fcfc_gpu_measure_fp64_peak.restype = C.c_double
         L.fcfc_gpu_measure_fp64_peak.argtypes = []
+        L.fcfc_gpu_measure_smem_atomic_peak.restype = C.c_double
+        L.fcfc_gpu_measure_smem_atomic_peak.argtypes = []
         L.fcfc_gpu_init.argtypes = [C.c_int, C.c_void_p, C.c_int]
         L.fcfc_gpu_set_option.argtypes = [C.c_char_p, C.c_long]
         _lib = L
@@ -272,6 +282,65 @@ class Catalog:
             pass
 
 
+class CatalogStream:
+    """A catalogue built chunk by chunk while the host is still reading the file (include/fcfc_gpu.h:
+    fcfc_gpu_catalog_stream_*): every :meth:`append` copies its rows to pinned staging memory and returns, the transfer
+    to the device overlaps the parsing of the next chunk (the chunk loop of io/read_ascii.c:750-950), and
+    :meth:`finish` returns the same :class:`Catalog` the one-shot constructor builds from the concatenated columns."""
+
+    def __init__(self, *, bins: Bins, weighted: bool = False, n_hint: int = 0, prescaled: bool = False):
+        self._bins, self._weighted, self._prescaled = bins, bool(weighted), prescaled
+        self._h = lib().fcfc_gpu_catalog_stream_begin(int(n_hint), int(bins.is_float), int(weighted))
+        if not self._h:
+            raise FcfcGpuError(last_error())
+
+    def __len__(self) -> int:
+        return lib().fcfc_gpu_catalog_stream_size(self._h) if self._h else 0
+
+    def append(self, x, y, z, w=None) -> None:
+        if not self._h:
+            raise FcfcGpuError("catalogue stream already finished")
+        dt = self._bins.dtype
+        xs = [np.ascontiguousarray(a, dtype=dt) for a in (x, y, z)]
+        n = len(xs[0])
+        if any(len(a) != n for a in xs):
+            raise ValueError("coordinate arrays differ in length")
+        if self._weighted != (w is not None):
+            raise ValueError("every chunk of a weighted stream needs weights (and only those)")
+        wv = np.ascontiguousarray(w, dtype=dt) if w is not None else None
+        if wv is not None and len(wv) != n:
+            raise ValueError("weights differ in length from the coordinates")
+        rc = lib().fcfc_gpu_catalog_stream_append(self._h, xs[0].ctypes.data, xs[1].ctypes.data, xs[2].ctypes.data,
+                                                  wv.ctypes.data if wv is not None else None, n)
+        if rc != 0:
+            raise FcfcGpuError(last_error(), rc)
+
+    def finish(self) -> Catalog:
+        if not self._h:
+            raise FcfcGpuError("catalogue stream already finished")
+        b = self._bins
+        n = len(self)
+        need_s = (not b.periodic) and b.bintype != BIN_ISO
+        h, self._h = self._h, None
+        cat = Catalog.__new__(Catalog)
+        cat.n, cat.has_w, cat.is_float = n, self._weighted, b.is_float
+        cat._h = lib().fcfc_gpu_catalog_stream_finish(h, 1.0 if self._prescaled else float(b.rescale), b.arith if need_s else -1)
+        if not cat._h:
+            raise FcfcGpuError(last_error())
+        return cat
+
+    def abort(self) -> None:
+        if getattr(self, "_h", None):
+            lib().fcfc_gpu_catalog_stream_abort(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.abort()
+        except Exception:
+            pass
+
+
 def count_pairs(cat1: Catalog, cat2: Catalog | None, bins: Bins, *, withwt: bool = False,
                 part: int = 0, nparts: int = 1, dev_hist_ptr: int | None = None) -> np.ndarray:
     """count_pairs(): raw pair counts (int64) or weighted sums (float64), ``ntot`` entries laid out as
@@ -317,4 +386,12 @@ def measure_fp64_peak() -> float:
     v = lib().fcfc_gpu_measure_fp64_peak()
     if v <= 0:
         raise FcfcGpuError("FP64 peak measurement failed (no device?)")
+    return v
+
+
+def measure_smem_atomic_peak() -> float:
+    """Shared-memory histogram increments per second (red.shared.add.u32 lanes, whole device)."""
+    v = lib().fcfc_gpu_measure_smem_atomic_peak()
+    if v <= 0:
+        raise FcfcGpuError("shared-memory atomic peak measurement failed (no device?)")
     return v

@@ -1243,6 +1243,38 @@ extern "C" void fcfc_gpu_finalize(void) {
   pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear();
 }
 
+// The second half of an upload, on columns that are already in device memory (c->x, y, z[, s][, w], n rows): rescale in
+// `real`, the survey's 4th coordinate when the metric needs it, bounding box, extreme |x|^2, sum of weights, the check
+// for non-finite coordinates -- one pass of prep_kernel (build_tree.c:121-140, 2pt/build_tree.c:35-133).  `s_given`: the
+// caller supplied x^2+y^2+z^2 (it is kept as it is).
+template <class T>
+static int catalog_prepare(DevCat *c, bool s_given, double rescale, int sumsq) {
+  const size_t n = c->n;
+  PoolScope pool;
+  unsigned long long *stats = nullptr; double *wsum = nullptr;
+  CUDA_TRY(pool.alloc(&stats, 10 * 8), FCFC_GPU_ERR_MEMORY);
+  wsum = reinterpret_cast<double *>(stats + 8);
+  unsigned long long init[10];
+  for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
+  init[6] = 0; init[7] = 0; init[8] = 0; init[9] = ~0ull;
+  CUDA_TRY(cudaMemcpy(stats, init, sizeof init, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
+  if (n) {
+    const int nb = (int) std::min<size_t>((n + 255) / 256, 148 * 8);
+    prep_kernel<T><<<nb, 256>>>((T *) c->x, (T *) c->y, (T *) c->z, (T *) c->s, n, (T) rescale, rescale != 1.0,
+                                s_given ? -1 : sumsq, stats, wsum, (const T *) c->w);
+    g_stats.kernel_launches++;
+  }
+  unsigned long long out[10];
+  CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
+  if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
+  for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
+  c->smax = n ? dec_f64(out[6]) : 0;
+  c->smin = n ? dec_f64(out[9]) : 0;
+  double ws; memcpy(&ws, &out[8], 8);
+  c->wsum = c->has_w ? ws : (double) n;
+  return 0;
+}
+
 // The catalogue columns arrive as host pointers (the FCFC host's malloc'd reader arrays) or as device pointers (a
 // launcher that all-gathered slices over NVLink): cudaMemcpyDefault resolves either through unified addressing.
 template <class T>
@@ -1265,29 +1297,7 @@ static int catalog_upload(DevCat *c, const void *x, const void *y, const void *z
     CUDA_TRY(pool_alloc(&c->w, bytes), FCFC_GPU_ERR_MEMORY);
     CUDA_TRY(cudaMemcpy(c->w, w, n * sizeof(T), cudaMemcpyDefault), FCFC_GPU_ERR_CUDA);
   }
-  PoolScope pool;
-  unsigned long long *stats = nullptr; double *wsum = nullptr;
-  CUDA_TRY(pool.alloc(&stats, 10 * 8), FCFC_GPU_ERR_MEMORY);
-  wsum = reinterpret_cast<double *>(stats + 8);
-  unsigned long long init[10];
-  for (int k = 0; k < 3; k++) { init[k] = ~0ull; init[3 + k] = 0; }
-  init[6] = 0; init[7] = 0; init[8] = 0; init[9] = ~0ull;
-  CUDA_TRY(cudaMemcpy(stats, init, sizeof init, cudaMemcpyHostToDevice), FCFC_GPU_ERR_CUDA);
-  if (n) {
-    const int nb = (int) std::min<size_t>((n + 255) / 256, 148 * 8);
-    prep_kernel<T><<<nb, 256>>>((T *) c->x, (T *) c->y, (T *) c->z, (T *) c->s, n, (T) rescale, rescale != 1.0,
-                                s ? -1 : sumsq, stats, wsum, (const T *) c->w);
-    g_stats.kernel_launches++;
-  }
-  unsigned long long out[10];
-  CUDA_TRY(cudaMemcpy(out, stats, sizeof out, cudaMemcpyDeviceToHost), FCFC_GPU_ERR_CUDA);
-  if (out[7]) { set_err("catalogue contains %llu non-finite coordinates", out[7]); return FCFC_GPU_ERR_DATA; }
-  for (int k = 0; k < 3; k++) { c->bmin[k] = n ? dec_f64(out[k]) : 0; c->bmax[k] = n ? dec_f64(out[3 + k]) : 0; }
-  c->smax = n ? dec_f64(out[6]) : 0;
-  c->smin = n ? dec_f64(out[9]) : 0;
-  double ws; memcpy(&ws, &out[8], 8);
-  c->wsum = w ? ws : (double) n;
-  return 0;
+  return catalog_prepare<T>(c, s != nullptr, rescale, sumsq);
 }
 
 // Replica of an uploaded (rescaled, checked) catalogue on another device: device-to-device copies over NVLink /
@@ -1309,6 +1319,23 @@ static int catalog_replicate(DevCat *dst, const DevCat *src, size_t real_bytes) 
   return 0;
 }
 
+// Replicas of a prepared first copy (c->dev[0]) on every other device in use, copied concurrently and complete on return.
+static int catalog_spread(fcfc_gpu_catalog *c) {
+  for (size_t i = 1; i < g_ctx.devices.size(); i++) {
+    DevCat *dc = new DevCat();
+    dc->is_float = c->is_float; dc->n = c->n; dc->device = g_ctx.devices[i];
+    c->dev.push_back(dc);
+    cudaSetDevice(dc->device);
+    const int e = catalog_replicate(dc, c->dev[0], c->is_float ? sizeof(float) : sizeof(double));
+    if (e) return e;
+  }
+  for (size_t i = 1; i < g_ctx.devices.size(); i++) {       // the replicas are complete before anyone counts on them
+    cudaSetDevice(g_ctx.devices[i]);
+    if (cudaStreamSynchronize(0) != cudaSuccess) { set_err("catalogue replication failed: %s", cudaGetErrorString(cudaGetLastError())); return FCFC_GPU_ERR_CUDA; }
+  }
+  return 0;
+}
+
 extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *y, const void *z, const void *x2sum,
                                                      const void *w, size_t n, int is_float, double rescale, int sumsq_arith) {
   if (ensure_init()) return nullptr;
@@ -1318,22 +1345,162 @@ extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_create(const void *x, const void *
   c->is_float = is_float; c->n = n; c->has_w = w != nullptr;
   // one replica per device: the first is uploaded from the caller's arrays and prepared (rescale, sums, bounding box,
   // checks) once; the others are copied from it device to device, concurrently
-  for (size_t i = 0; i < g_ctx.devices.size(); i++) {
-    const int d = g_ctx.devices[i];
-    DevCat *dc = new DevCat();
-    dc->is_float = is_float; dc->n = n; dc->device = d;
-    c->dev.push_back(dc);
-    cudaSetDevice(d);
-    int e;
-    if (i == 0) e = is_float ? catalog_upload<float>(dc, x, y, z, x2sum, w, rescale, sumsq_arith)
-                             : catalog_upload<double>(dc, x, y, z, x2sum, w, rescale, sumsq_arith);
-    else e = catalog_replicate(dc, c->dev[0], is_float ? sizeof(float) : sizeof(double));
-    if (e) { fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
+  DevCat *dc = new DevCat();
+  dc->is_float = is_float; dc->n = n; dc->device = g_ctx.devices[0];
+  c->dev.push_back(dc);
+  cudaSetDevice(dc->device);
+  int e = is_float ? catalog_upload<float>(dc, x, y, z, x2sum, w, rescale, sumsq_arith)
+                   : catalog_upload<double>(dc, x, y, z, x2sum, w, rescale, sumsq_arith);
+  if (!e) e = catalog_spread(c);
+  if (e) { fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
+  c->wsum = c->dev[0]->wsum;
+  cudaSetDevice(g_ctx.devices[0]);
+  return c;
+}
+
+// ------------------------------------------------------------------------------------------
+// Streamed ingest.  The reference's readers fill the catalogue columns chunk by chunk
+// (src/io/read_ascii.c:750-950: fread a chunk, parse its lines, append to res[i]) and only then does tree_create rescale
+// and index them (2pt_box/build_tree.c:84-156).  With this interface the reader hands every parsed chunk over as soon as it
+// exists: the rows are copied into one of a few pinned staging slots and sent to the device with cudaMemcpyAsync on a
+// private stream, so the transfer of chunk k overlaps the parsing of chunk k + 1 and the catalogue is resident when the
+// file ends.  finish() then runs the same prep_kernel pass as the one-shot upload and spreads the replicas.
+struct fcfc_gpu_catalog_stream {
+  int is_float = 0, has_w = 0, device = 0;
+  size_t rb = 8;                  // bytes per value
+  size_t n = 0, cap = 0;          // rows appended / rows the device columns hold
+  void *col[4] = {nullptr, nullptr, nullptr, nullptr};      // x, y, z, w on the device (pool blocks)
+  int ncol = 3;
+  cudaStream_t stream = nullptr;
+  static constexpr int kSlots = 3;
+  static constexpr size_t kSlotRows = (size_t) 1 << 18;     // 256 Ki rows per slot: 3-8 MB per transfer
+  unsigned char *pinned = nullptr;
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};
+  bool busy[kSlots] = {false, false, false};
+  int next = 0;
+  bool failed = false;
+};
+
+static void stream_release(fcfc_gpu_catalog_stream *b) {
+  if (!b) return;
+  cudaSetDevice(b->device);
+  if (b->stream) cudaStreamSynchronize(b->stream);
+  for (auto &e : b->done) if (e) cudaEventDestroy(e);
+  if (b->stream) cudaStreamDestroy(b->stream);
+  if (b->pinned) cudaFreeHost(b->pinned);
+  for (auto &p : b->col) pool_free(p);
+  cudaGetLastError();
+  delete b;
+}
+
+// device columns for at least `rows` rows; rows already appended are carried over (device to device, stream order)
+static int stream_reserve(fcfc_gpu_catalog_stream *b, size_t rows) {
+  if (rows <= b->cap) return 0;
+  size_t cap = std::max<size_t>(rows, std::max<size_t>(2 * b->cap, 1024));
+  void *fresh[4] = {nullptr, nullptr, nullptr, nullptr};
+  for (int k = 0; k < b->ncol; k++) {
+    cudaError_t e = pool_alloc(&fresh[k], cap * b->rb);
+    if (e != cudaSuccess) {
+      for (int j = 0; j < k; j++) pool_free(fresh[j]);
+      set_err("out of device memory while growing a streamed catalogue to %zu rows: %s", cap, cudaGetErrorString(e));
+      cudaGetLastError();
+      return FCFC_GPU_ERR_MEMORY;
+    }
+    if (b->n) CUDA_TRY(cudaMemcpyAsync(fresh[k], b->col[k], b->n * b->rb, cudaMemcpyDeviceToDevice, b->stream), FCFC_GPU_ERR_CUDA);
   }
-  for (size_t i = 1; i < g_ctx.devices.size(); i++) {       // the replicas are complete before anyone counts on them
-    cudaSetDevice(g_ctx.devices[i]);
-    if (cudaStreamSynchronize(0) != cudaSuccess) { set_err("catalogue replication failed: %s", cudaGetErrorString(cudaGetLastError())); fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
+  if (b->cap) CUDA_TRY(cudaStreamSynchronize(b->stream), FCFC_GPU_ERR_CUDA);     // the old blocks go back to the pool: nothing may still read them
+  for (int k = 0; k < b->ncol; k++) { pool_free(b->col[k]); b->col[k] = fresh[k]; }
+  b->cap = cap;
+  return 0;
+}
+
+extern "C" fcfc_gpu_catalog_stream *fcfc_gpu_catalog_stream_begin(size_t n_hint, int is_float, int with_weight) {
+  if (ensure_init()) return nullptr;
+  fcfc_gpu_catalog_stream *b = new fcfc_gpu_catalog_stream();
+  b->is_float = is_float != 0; b->has_w = with_weight != 0; b->rb = is_float ? sizeof(float) : sizeof(double);
+  b->ncol = with_weight ? 4 : 3;
+  b->device = g_ctx.devices[0];
+  cudaSetDevice(b->device);
+  const size_t slot_bytes = fcfc_gpu_catalog_stream::kSlotRows * b->rb * (size_t) b->ncol;
+  cudaError_t e = cudaStreamCreate(&b->stream);      // (blocking flavour: ordered after whatever the default stream still does with recycled pool blocks)
+  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&b->pinned), slot_bytes * fcfc_gpu_catalog_stream::kSlots);
+  for (int k = 0; e == cudaSuccess && k < fcfc_gpu_catalog_stream::kSlots; k++) e = cudaEventCreateWithFlags(&b->done[k], cudaEventDisableTiming);
+  if (e != cudaSuccess) { set_err("streamed ingest: %s", cudaGetErrorString(e)); cudaGetLastError(); stream_release(b); return nullptr; }
+  if (n_hint && stream_reserve(b, n_hint)) { stream_release(b); return nullptr; }
+  return b;
+}
+
+extern "C" int fcfc_gpu_catalog_stream_append(fcfc_gpu_catalog_stream *b, const void *x, const void *y, const void *z,
+                                              const void *w, size_t n) {
+  if (!b) { set_err("NULL catalogue stream"); return FCFC_GPU_ERR_ARG; }
+  if (b->failed) { set_err("catalogue stream is in a failed state"); return FCFC_GPU_ERR_ARG; }
+  if (n == 0) return 0;
+  if (!x || !y || !z || (b->has_w && !w)) { set_err("NULL column in a chunk of %zu rows", n); return FCFC_GPU_ERR_ARG; }
+  if (b->n + n >= (1ull << 31) - 64) { set_err("catalogue too large for 32-bit point indices"); return FCFC_GPU_ERR_ARG; }
+  cudaSetDevice(b->device);
+  int e = stream_reserve(b, b->n + n);
+  if (e) { b->failed = true; return e; }
+  const void *src[4] = {x, y, z, w};
+  const size_t slot_rows = fcfc_gpu_catalog_stream::kSlotRows, slot_bytes = slot_rows * b->rb * (size_t) b->ncol;
+  for (size_t off = 0; off < n; off += slot_rows) {
+    const size_t m = std::min(slot_rows, n - off);
+    const int slot = b->next;
+    b->next = (b->next + 1) % fcfc_gpu_catalog_stream::kSlots;
+    if (b->busy[slot]) {          // the transfer that last used this slot must have left it
+      cudaError_t ce = cudaEventSynchronize(b->done[slot]);
+      if (ce != cudaSuccess) { b->failed = true; set_err("streamed ingest: %s", cudaGetErrorString(ce)); cudaGetLastError(); return FCFC_GPU_ERR_CUDA; }
+    }
+    unsigned char *stage = b->pinned + (size_t) slot * slot_bytes;
+    for (int k = 0; k < b->ncol; k++) {
+      unsigned char *h = stage + (size_t) k * slot_rows * b->rb;
+      memcpy(h, static_cast<const unsigned char *>(src[k]) + off * b->rb, m * b->rb);
+      cudaError_t ce = cudaMemcpyAsync(static_cast<unsigned char *>(b->col[k]) + (b->n + off) * b->rb, h, m * b->rb, cudaMemcpyHostToDevice, b->stream);
+      if (ce != cudaSuccess) { b->failed = true; set_err("streamed ingest: %s", cudaGetErrorString(ce)); cudaGetLastError(); return FCFC_GPU_ERR_CUDA; }
+    }
+    cudaEventRecord(b->done[slot], b->stream);
+    b->busy[slot] = true;
   }
+  b->n += n;
+  return 0;
+}
+
+extern "C" size_t fcfc_gpu_catalog_stream_size(const fcfc_gpu_catalog_stream *b) { return b ? b->n : 0; }
+
+extern "C" void fcfc_gpu_catalog_stream_abort(fcfc_gpu_catalog_stream *b) {
+  stream_release(b);
+  if (g_ctx.ready && !g_ctx.devices.empty()) cudaSetDevice(g_ctx.devices[0]);
+}
+
+extern "C" fcfc_gpu_catalog *fcfc_gpu_catalog_stream_finish(fcfc_gpu_catalog_stream *b, double rescale, int sumsq_arith) {
+  if (!b) { set_err("NULL catalogue stream"); return nullptr; }
+  if (b->failed) { set_err("catalogue stream is in a failed state"); stream_release(b); return nullptr; }
+  cudaSetDevice(b->device);
+  if (stream_reserve(b, 1)) { stream_release(b); return nullptr; }      // (an empty catalogue still owns valid columns)
+  if (cudaStreamSynchronize(b->stream) != cudaSuccess) {
+    set_err("streamed ingest: %s", cudaGetErrorString(cudaGetLastError()));
+    stream_release(b);
+    return nullptr;
+  }
+  fcfc_gpu_catalog *c = new fcfc_gpu_catalog();
+  c->is_float = b->is_float; c->n = b->n; c->has_w = b->has_w != 0;
+  DevCat *dc = new DevCat();
+  dc->is_float = b->is_float; dc->n = b->n; dc->device = b->device;
+  dc->x = b->col[0]; dc->y = b->col[1]; dc->z = b->col[2]; dc->w = b->col[3];     // ownership of the columns passes to the catalogue
+  for (auto &p : b->col) p = nullptr;
+  dc->has_w = b->has_w != 0;
+  c->dev.push_back(dc);
+  const int is_float = b->is_float;
+  stream_release(b);
+  cudaSetDevice(dc->device);
+  int e = 0;
+  dc->has_s = sumsq_arith >= 0;
+  if (dc->has_s) {
+    cudaError_t ce = pool_alloc(&dc->s, (dc->n ? dc->n : 1) * (is_float ? sizeof(float) : sizeof(double)));
+    if (ce != cudaSuccess) { set_err("out of device memory: %s", cudaGetErrorString(ce)); cudaGetLastError(); e = FCFC_GPU_ERR_MEMORY; }
+  }
+  if (!e) e = is_float ? catalog_prepare<float>(dc, false, rescale, sumsq_arith) : catalog_prepare<double>(dc, false, rescale, sumsq_arith);
+  if (!e) e = catalog_spread(c);
+  if (e) { fcfc_gpu_catalog_destroy(c); cudaSetDevice(g_ctx.devices[0]); return nullptr; }
   c->wsum = c->dev[0]->wsum;
   cudaSetDevice(g_ctx.devices[0]);
   return c;

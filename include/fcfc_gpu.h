@@ -134,6 +134,28 @@ size_t fcfc_gpu_catalog_size(const fcfc_gpu_catalog *cat);
 /* Sum of weights accumulated in double (data->wt, build_tree.c:133-140); n if unweighted. */
 double fcfc_gpu_catalog_wsum(const fcfc_gpu_catalog *cat);
 
+/* Streamed ingest: the same catalogue built chunk by chunk while the host is still reading the file, replacing the
+ * "read everything, then index" order of tree_create (fcfc/2pt_box/build_tree.c:84-156) around the chunk loop of the
+ * readers (io/read_ascii.c:750-950: fread a chunk, parse its lines, append to the columns).
+ *   _begin:  n_hint = expected number of rows (0: unknown, the device columns grow geometrically); with_weight != 0 when
+ *            every chunk carries a weight column.
+ *   _append: n rows of `real` per column (host pointers, unrescaled or rescaled as the caller prefers); the rows are
+ *            copied into pinned staging memory before the call returns -- the caller may reuse or realloc() its arrays
+ *            at once -- and travel to the device asynchronously, overlapping whatever the host does next.  n = 0 is a
+ *            no-op.  After an error the stream only accepts _abort / _finish (which then fails).
+ *   _finish: waits for the transfers, runs the one pass over the columns that fcfc_gpu_catalog_create runs (rescale in
+ *            `real` when rescale != 1, x^2+y^2+z^2 in the order `sumsq_arith` selects when >= 0, bounding box, sum of
+ *            weights, non-finite check), replicates the catalogue on the other devices in use and returns the handle
+ *            (NULL on failure).  The stream object is released either way.
+ *   _abort:  releases a stream without building a catalogue. */
+typedef struct fcfc_gpu_catalog_stream fcfc_gpu_catalog_stream;
+fcfc_gpu_catalog_stream *fcfc_gpu_catalog_stream_begin(size_t n_hint, int is_float, int with_weight);
+int fcfc_gpu_catalog_stream_append(fcfc_gpu_catalog_stream *st, const void *x, const void *y, const void *z,
+    const void *w, size_t n);
+size_t fcfc_gpu_catalog_stream_size(const fcfc_gpu_catalog_stream *st);
+fcfc_gpu_catalog *fcfc_gpu_catalog_stream_finish(fcfc_gpu_catalog_stream *st, double rescale, int sumsq_arith);
+void fcfc_gpu_catalog_stream_abort(fcfc_gpu_catalog_stream *st);
+
 /* count_pairs(): full count over all devices in use; the per-device partial histograms are
  * combined with one all-reduce.  Exactly one of cnt_i / cnt_d is written (ntot entries,
  * overwritten, not accumulated): cnt_i when !withwt, cnt_d when withwt. */
@@ -184,6 +206,10 @@ int fcfc_gpu_cnvt_coord(void *x, void *y, void *z, size_t n, int is_float, doubl
 double fcfc_gpu_measure_fp32_peak(double *sm_clock_mhz_out);
 /* The same for FP64 (DFMA stream): the denominator for the double-precision kernels. */
 double fcfc_gpu_measure_fp64_peak(void);
+/* Shared-memory histogram increments per second (red.shared.add.u32 lanes on pseudo-random bins of a 4800-counter
+ * histogram, whole device): every accepted pair costs one, so in-range pairs / this rate is the time the histogram
+ * update alone needs -- the second bound bench.py states next to the FP32 issue roofline (`roofline.ceiling`). */
+double fcfc_gpu_measure_smem_atomic_peak(void);
 /* Diagnostics: the fixed-point scales 2^ks, 2^km the counting kernels use for their computed s and mu bins
  * (host arithmetic only; the CPU tests check the error budget behind them). */
 void fcfc_gpu_fastbin_scales(int ns, int nmu, int periodic, int *ks, int *km);

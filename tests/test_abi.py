@@ -44,6 +44,8 @@ def test_no_cpu_fallback_without_device():
     b = F.Bins(periodic=True, bintype=0, smax=10.0, ds=1.0, box=100.0)
     with pytest.raises(F.FcfcGpuError):
         F.Catalog([1.0], [2.0], [3.0], bins=b)
+    with pytest.raises(F.FcfcGpuError):
+        F.CatalogStream(bins=b)
 
 
 def test_product_never_imports_the_oracle():
