@@ -1406,9 +1406,19 @@ static int stream_reserve(fcfc_gpu_catalog_stream *b, size_t rows) {
       cudaGetLastError();
       return FCFC_GPU_ERR_MEMORY;
     }
-    if (b->n) CUDA_TRY(cudaMemcpyAsync(fresh[k], b->col[k], b->n * b->rb, cudaMemcpyDeviceToDevice, b->stream), FCFC_GPU_ERR_CUDA);
+    if (b->n && e == cudaSuccess) e = cudaMemcpyAsync(fresh[k], b->col[k], b->n * b->rb, cudaMemcpyDeviceToDevice, b->stream);
+    if (e != cudaSuccess) {
+      for (int j = 0; j <= k; j++) pool_free(fresh[j]);
+      set_err("streamed ingest: %s", cudaGetErrorString(e));
+      cudaGetLastError();
+      return FCFC_GPU_ERR_CUDA;
+    }
   }
-  if (b->cap) CUDA_TRY(cudaStreamSynchronize(b->stream), FCFC_GPU_ERR_CUDA);     // the old blocks go back to the pool: nothing may still read them
+  if (b->cap && cudaStreamSynchronize(b->stream) != cudaSuccess) {      // the old blocks go back to the pool: nothing may still read them
+    for (int k = 0; k < b->ncol; k++) pool_free(fresh[k]);
+    set_err("streamed ingest: %s", cudaGetErrorString(cudaGetLastError()));
+    return FCFC_GPU_ERR_CUDA;
+  }
   for (int k = 0; k < b->ncol; k++) { pool_free(b->col[k]); b->col[k] = fresh[k]; }
   b->cap = cap;
   return 0;
@@ -1426,6 +1436,7 @@ extern "C" fcfc_gpu_catalog_stream *fcfc_gpu_catalog_stream_begin(size_t n_hint,
   if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&b->pinned), slot_bytes * fcfc_gpu_catalog_stream::kSlots);
   for (int k = 0; e == cudaSuccess && k < fcfc_gpu_catalog_stream::kSlots; k++) e = cudaEventCreateWithFlags(&b->done[k], cudaEventDisableTiming);
   if (e != cudaSuccess) { set_err("streamed ingest: %s", cudaGetErrorString(e)); cudaGetLastError(); stream_release(b); return nullptr; }
+  n_hint = std::min<size_t>(n_hint, ((size_t) 1 << 31) - 65);       // (a hint, not a promise: append() enforces the limit)
   if (n_hint && stream_reserve(b, n_hint)) { stream_release(b); return nullptr; }
   return b;
 }
