@@ -1237,9 +1237,11 @@ extern "C" int fcfc_gpu_init(int ndev, const int *devices, int verbose) {
   return (int) g_ctx.devices.size();
 }
 
+static void stage_release_all();       // pinned staging block of the streamed ingest (below)
 extern "C" void fcfc_gpu_finalize(void) {
   for (int d : g_ctx.devices) { cudaSetDevice(d); cudaDeviceSynchronize(); }
   nccl_reset();
+  stage_release_all();
   pool_release_all(); g_ctx.ready = false; g_ctx.devices.clear();
 }
 
@@ -1372,14 +1374,48 @@ struct fcfc_gpu_catalog_stream {
   void *col[4] = {nullptr, nullptr, nullptr, nullptr};      // x, y, z, w on the device (pool blocks)
   int ncol = 3;
   cudaStream_t stream = nullptr;
-  static constexpr int kSlots = 3;
-  static constexpr size_t kSlotRows = (size_t) 1 << 18;     // 256 Ki rows per slot: 3-8 MB per transfer
+  static constexpr int kSlots = 4;
+  static constexpr size_t kSlotRows = (size_t) 1 << 16;     // 64 Ki rows per slot and column: transfers of 256-512 KB
   unsigned char *pinned = nullptr;
-  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr};
-  bool busy[kSlots] = {false, false, false};
+  size_t pinned_bytes = 0;
+  cudaEvent_t done[kSlots] = {nullptr, nullptr, nullptr, nullptr};
+  bool busy[kSlots] = {false, false, false, false};
   int next = 0;
   bool failed = false;
 };
+
+// The pinned staging block of the last finished stream is kept for the next one (cudaMallocHost costs ~1 ms per MB: a
+// program reads two or three catalogues in a row); fcfc_gpu_finalize gives it back.
+static std::mutex g_stage_mutex;
+static unsigned char *g_stage_cached = nullptr;
+static size_t g_stage_cached_bytes = 0;
+static unsigned char *stage_take(size_t bytes, size_t *got) {
+  {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (g_stage_cached && g_stage_cached_bytes >= bytes) {
+      unsigned char *p = g_stage_cached; *got = g_stage_cached_bytes;
+      g_stage_cached = nullptr; g_stage_cached_bytes = 0;
+      return p;
+    }
+  }
+  unsigned char *p = nullptr;
+  if (cudaMallocHost(reinterpret_cast<void **>(&p), bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  *got = bytes;
+  return p;
+}
+static void stage_give(unsigned char *p, size_t bytes) {
+  if (!p) return;
+  {
+    std::lock_guard<std::mutex> lock(g_stage_mutex);
+    if (!g_stage_cached || g_stage_cached_bytes < bytes) { std::swap(p, g_stage_cached); std::swap(bytes, g_stage_cached_bytes); }
+  }
+  if (p) cudaFreeHost(p);
+}
+static void stage_release_all() {
+  std::lock_guard<std::mutex> lock(g_stage_mutex);
+  if (g_stage_cached) cudaFreeHost(g_stage_cached);
+  g_stage_cached = nullptr; g_stage_cached_bytes = 0;
+}
 
 static void stream_release(fcfc_gpu_catalog_stream *b) {
   if (!b) return;
@@ -1387,7 +1423,7 @@ static void stream_release(fcfc_gpu_catalog_stream *b) {
   if (b->stream) cudaStreamSynchronize(b->stream);
   for (auto &e : b->done) if (e) cudaEventDestroy(e);
   if (b->stream) cudaStreamDestroy(b->stream);
-  if (b->pinned) cudaFreeHost(b->pinned);
+  stage_give(b->pinned, b->pinned_bytes);
   for (auto &p : b->col) pool_free(p);
   cudaGetLastError();
   delete b;
@@ -1433,7 +1469,7 @@ extern "C" fcfc_gpu_catalog_stream *fcfc_gpu_catalog_stream_begin(size_t n_hint,
   cudaSetDevice(b->device);
   const size_t slot_bytes = fcfc_gpu_catalog_stream::kSlotRows * b->rb * (size_t) b->ncol;
   cudaError_t e = cudaStreamCreate(&b->stream);      // (blocking flavour: ordered after whatever the default stream still does with recycled pool blocks)
-  if (e == cudaSuccess) e = cudaMallocHost(reinterpret_cast<void **>(&b->pinned), slot_bytes * fcfc_gpu_catalog_stream::kSlots);
+  if (e == cudaSuccess && !(b->pinned = stage_take(slot_bytes * fcfc_gpu_catalog_stream::kSlots, &b->pinned_bytes))) e = cudaErrorMemoryAllocation;
   for (int k = 0; e == cudaSuccess && k < fcfc_gpu_catalog_stream::kSlots; k++) e = cudaEventCreateWithFlags(&b->done[k], cudaEventDisableTiming);
   if (e != cudaSuccess) { set_err("streamed ingest: %s", cudaGetErrorString(e)); cudaGetLastError(); stream_release(b); return nullptr; }
   n_hint = std::min<size_t>(n_hint, ((size_t) 1 << 31) - 65);       // (a hint, not a promise: append() enforces the limit)

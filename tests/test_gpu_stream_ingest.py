@@ -66,7 +66,7 @@ def stream_catalog(F, cols, bins, chunks, n_hint=0, weighted=False, reuse_buffer
 @pytest.mark.parametrize("withwt", [False, True])
 def test_streamed_box_catalogue_equals_one_shot(gpu, prec, withwt):
     F = gpu
-    n = 300_000                 # more than one pinned slot (2^18 rows)
+    n = 300_000                 # more than the four pinned slots together (2^16 rows each)
     cols = box_catalog(n, 500.0, 91, weights=True)
     b = F.Bins(periodic=True, prec=prec, arith=1, **BOX_KW)
     one = F.Catalog(*cols[:3], cols[3] if withwt else None, bins=b)
