@@ -52,3 +52,24 @@ def test_in_process_multi_device_matches_single_device():
     np.testing.assert_allclose(res["all"][2], res["one"][2], rtol=1e-12, atol=0)
     np.testing.assert_array_equal(res["one"][3], res["all"][3])
     assert res["one"][0].sum() > 0
+
+
+@pytest.mark.skipif(_ndev() < 2, reason="needs at least two GPUs")
+def test_streamed_catalogue_is_replicated_on_every_device():
+    """Streamed ingest (fcfc_gpu_catalog_stream_*) lands on the first device and is copied to the others like a one-shot
+    upload: the sharded count over all devices equals the single-device count."""
+    import fcfc_b200 as F
+    x, y, z, _ = box_catalog(200000, 600.0, 94)
+    res = {}
+    for tag, devs in (("one", [0]), ("all", None)):
+        F.init(devices=devs)
+        b = F.Bins(periodic=True, prec="float", arith=1, box=600.0, bintype=1, smax=60.0, ds=1.5, nmu=60)
+        st = F.CatalogStream(bins=b, n_hint=1000)
+        for lo in range(0, len(x), 30011):
+            st.append(x[lo:lo + 30011], y[lo:lo + 30011], z[lo:lo + 30011])
+        g = st.finish()
+        res[tag] = F.count_pairs(g, None, b)
+        g.destroy()
+    F.init(devices=[0])
+    np.testing.assert_array_equal(res["one"], res["all"])
+    assert res["one"].sum() > 0
